@@ -1,0 +1,57 @@
+// Library-level entry points of libtavk.so: error string, version, device probe.
+// There is no CPU fallback anywhere in this library: tavk_device_check() is what the Python host calls at import
+// time on a GPU box, and every compute entry point enqueues sm_100a-only kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/tavk.h"
+#include "common.cuh"
+
+namespace tavk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace tavk
+
+extern "C" const char* tavk_last_error(void) { return tavk::g_err; }
+
+extern "C" int tavk_version(void) { return TAVK_VERSION; }
+
+extern "C" int tavk_sm_count(void) { return tavk::sm_count(); }
+
+extern "C" int tavk_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        tavk::set_error("tavk_device_check: no CUDA device (%s)", cudaGetErrorString(e));
+        return 3;
+    }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) {
+        tavk::set_error("tavk_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev, major,
+                        minor);
+        return 3;
+    }
+    return 0;
+}

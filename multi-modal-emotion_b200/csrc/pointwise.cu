@@ -1,0 +1,422 @@
+// HBM-bound helper kernels of the TAV path: modality-embedding add, sequence mean-pool, (weighted) column sums,
+// launch-bound fp32 small linears (classifier head, rank-1 attention term), casts, scaling and head dropout.
+// All are coalesced float4 / 8-byte bf16 accesses; grids are sized from the SM count.
+#include "../../include/tavk.h"
+#include "common.cuh"
+
+namespace tavk {
+
+// ---------------------------------------------------------------- embed add (models/tav.py:474)
+__global__ void embed_add_fwd_kernel(const float4* __restrict__ x, const int64_t* __restrict__ idx,
+                                     const float4* __restrict__ table, float4* __restrict__ y, int rows, int H4,
+                                     int n_embed) {
+    const long long total = (long long)rows * H4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / H4);
+        const int c = (int)(i - (long long)row * H4);
+        long long j = idx[row];
+        j = j < 0 ? 0 : (j >= n_embed ? n_embed - 1 : j);
+        const float4 a = x[i];
+        const float4 t = __ldg(table + j * H4 + c);
+        y[i] = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+    }
+}
+
+// dtable[j, c] += sum over rows with idx == j; block = 256 columns-quads slab, rows chunked over blockIdx.y
+__global__ void embed_add_bwd_kernel(const float* __restrict__ dy, const int64_t* __restrict__ idx,
+                                     float* __restrict__ dtable, int rows, int H, int n_embed, int rows_per_chunk) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    const int r0 = blockIdx.y * rows_per_chunk;
+    const int r1 = min(r0 + rows_per_chunk, rows);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = r0; r < r1; ++r) {
+        const int j = (int)idx[r];
+        const float v = dy[(size_t)r * H + c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += (k == j) ? v : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < n_embed && acc[k] != 0.f) atomicAdd(dtable + (size_t)k * H + c, acc[k]);
+}
+
+// ---------------------------------------------------------------- mean pool (models/tav.py:478,481,488)
+__global__ void mean_pool_fwd_kernel(const float4* __restrict__ x, float* __restrict__ y, int S, int H4,
+                                     int rows_per_chunk, float inv_s) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H4) return;
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.y * rows_per_chunk;
+    const int s1 = min(s0 + rows_per_chunk, S);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* xb = x + (size_t)b * S * H4;
+    for (int s = s0; s < s1; ++s) {
+        const float4 v = xb[(size_t)s * H4 + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = y + ((size_t)b * H4 + c) * 4;
+    atomicAdd(o + 0, acc.x * inv_s);
+    atomicAdd(o + 1, acc.y * inv_s);
+    atomicAdd(o + 2, acc.z * inv_s);
+    atomicAdd(o + 3, acc.w * inv_s);
+}
+
+__global__ void mean_pool_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx,
+                                     uint2* __restrict__ dx_bf16, int S, int H4, long long total, float inv_s) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / H4;
+        const int c = (int)(i - row * H4);
+        const int b = (int)(row / S);
+        float4 v = __ldg(dy + (size_t)b * H4 + c);
+        v.x *= inv_s; v.y *= inv_s; v.z *= inv_s; v.w *= inv_s;
+        if (dx) dx[i] = v;
+        if (dx_bf16) dx_bf16[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+// ---------------------------------------------------------------- (weighted) column sums
+// out[b, n] (+)= sum_{s in chunk} w[b,s] * x[b,s,n]; each thread owns 4 consecutive columns.
+template <bool BF16>
+__global__ void colsum_kernel(const void* __restrict__ x_, long long ld, const float* __restrict__ w,
+                              float* __restrict__ out, int S, int N, int rows_per_chunk) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 * 4 >= N) return;
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.y * rows_per_chunk;
+    const int s1 = min(s0 + rows_per_chunk, S);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* wb = w ? w + (size_t)b * S : nullptr;
+    for (int s = s0; s < s1; ++s) {
+        const float ws = wb ? wb[s] : 1.0f;
+        float4 v;
+        if (BF16) {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) +
+                                                           ((size_t)b * S + s) * ld + c4 * 4);
+            const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+            v = make_float4(a.x, a.y, c.x, c.y);
+        } else {
+            v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + ((size_t)b * S + s) * ld + c4 * 4);
+        }
+        acc.x += ws * v.x; acc.y += ws * v.y; acc.z += ws * v.z; acc.w += ws * v.w;
+    }
+    float* o = out + (size_t)b * N + c4 * 4;
+    atomicAdd(o + 0, acc.x);
+    atomicAdd(o + 1, acc.y);
+    atomicAdd(o + 2, acc.z);
+    atomicAdd(o + 3, acc.w);
+}
+
+static int launch_colsum(const void* x, int x_dtype, long long ld, const float* w, float* out, int B, int S, int N,
+                         int accumulate, cudaStream_t stream) {
+    TAVK_CHECK(x && out, 1, "colsum: null pointer");
+    TAVK_CHECK(x_dtype == TAVK_F32 || x_dtype == TAVK_BF16, 1, "colsum: bad dtype");
+    TAVK_CHECK(N % 4 == 0 && ld % 4 == 0, 1, "colsum: N and ld must be multiples of 4 (N=%d ld=%lld)", N, ld);
+    if (B <= 0 || N <= 0) return 0;
+    if (!accumulate) TAVK_CUDA(cudaMemsetAsync(out, 0, (size_t)B * N * sizeof(float), stream));
+    if (S <= 0) return 0;
+    const int threads = 128;
+    const int gx = (N / 4 + threads - 1) / threads;
+    // enough row chunks to fill the machine ~2x
+    int chunks = (2 * sm_count() + gx * B - 1) / (gx * B);
+    if (chunks < 1) chunks = 1;
+    int rows_per_chunk = (S + chunks - 1) / chunks;
+    if (rows_per_chunk < 8) rows_per_chunk = 8;
+    chunks = (S + rows_per_chunk - 1) / rows_per_chunk;
+    dim3 grid(gx, chunks, B);
+    if (x_dtype == TAVK_BF16) colsum_kernel<true><<<grid, threads, 0, stream>>>(x, ld, w, out, S, N, rows_per_chunk);
+    else                      colsum_kernel<false><<<grid, threads, 0, stream>>>(x, ld, w, out, S, N, rows_per_chunk);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- small fp32 linears
+// y[m,n] = sum_k x[m,k] w[n,k] + b[n]; one warp per output element.
+__global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ b, float* __restrict__ y, int M, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const long long o = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (o >= (long long)M * N) return;
+    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
+    const float* xr = x + (size_t)m * K;
+    const float* wr = w + (size_t)n * K;
+    float s = 0.f;
+    if ((K & 3) == 0) {
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + k);
+            const float4 c = __ldg(reinterpret_cast<const float4*>(wr + k));
+            s += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
+        }
+    } else {
+        for (int k = lane; k < K; k += 32) s += xr[k] * wr[k];
+    }
+    s = warp_sum(s);
+    if (lane == 0) y[o] = s + (b ? b[n] : 0.f);
+}
+// dx[m,k] (+)= sum_n dy[m,n] w[n,k]; one thread per (m,k)
+__global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                          float* __restrict__ dx, int M, int N, int K, int accumulate) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)M * K) return;
+    const int m = (int)(i / K), k = (int)(i - (long long)m * K);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dy[(size_t)m * N + n] * __ldg(w + (size_t)n * K + k);
+    dx[i] = accumulate ? dx[i] + s : s;
+}
+// dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n,k)
+__global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                          float* __restrict__ dw, float* __restrict__ db, int M, int N, int K) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * K) return;
+    const int n = (int)(i / K), k = (int)(i - (long long)n * K);
+    float s = 0.f, sb = 0.f;
+    for (int m = 0; m < M; ++m) {
+        const float d = dy[(size_t)m * N + n];
+        s += d * x[(size_t)m * K + k];
+        sb += d;
+    }
+    if (dw) dw[i] += s;
+    if (db && k == 0) db[n] += sb;
+}
+
+// ---------------------------------------------------------------- casts / scaling / dropout
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long i = t; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    for (long long i = (n4 << 2) + t; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict__ y, float scale, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) y[i] = x[i] * scale;
+}
+TAVK_DEVINL float uniform01(uint64_t seed, uint64_t ctr) {
+    // splitmix64 finaliser over a Weyl sequence: counter-based, reproducible for (seed, offset + index)
+    uint64_t z = seed + (ctr + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ keep,
+                                   long long n, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool k = uniform01(seed, offset + (uint64_t)i) >= p;
+        keep[i] = k ? 1 : 0;
+        y[i] = k ? x[i] * inv_keep : 0.f;
+    }
+}
+__global__ void dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ keep,
+                                   float* __restrict__ dx, long long n, float inv_keep) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+        dx[i] = keep[i] ? dy[i] * inv_keep : 0.f;
+}
+
+// [B,S,nh,d] -> [B,nh,d,S] (the reference MultiHeadAttention "concat" quirk, utils/TAVFormer.py:86)
+// via a 32x32 smem transpose of the (S, d) plane of every (b, h); `inverse` maps back (used in backward).
+__global__ void permute_bshd_bhds_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int S,
+                                         int nh, int d, int inverse) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int bh = blockIdx.z;
+    const int b = bh / nh, h = bh % nh;
+    const int s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    if (!inverse) {
+        for (int j = ty; j < 32; j += 8) {
+            const int s = s0 + j, dd = d0 + tx;
+            if (s < S && dd < d) tile[j][tx] = in[(((size_t)b * S + s) * nh + h) * d + dd];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int dd = d0 + j, s = s0 + tx;
+            if (s < S && dd < d) out[(((size_t)b * nh + h) * d + dd) * S + s] = tile[tx][j];
+        }
+    } else {
+        for (int j = ty; j < 32; j += 8) {
+            const int dd = d0 + j, s = s0 + tx;
+            if (s < S && dd < d) tile[tx][j] = in[(((size_t)b * nh + h) * d + dd) * S + s];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int s = s0 + j, dd = d0 + tx;
+            if (s < S && dd < d) out[(((size_t)b * S + s) * nh + h) * d + dd] = tile[j][tx];
+        }
+    }
+}
+
+static inline int grid_for(long long n, int threads) {
+    long long g = (n + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace tavk
+
+using namespace tavk;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int tavk_embed_add_fwd(const float* x, const int64_t* idx, const float* table, float* y, int rows, int H,
+                                  int n_embed, void* stream) {
+    TAVK_CHECK(x && idx && table && y, 1, "tavk_embed_add_fwd: null pointer");
+    TAVK_CHECK(H % 4 == 0 && n_embed >= 1, 1, "tavk_embed_add_fwd: H=%d must be a multiple of 4", H);
+    if (rows <= 0) return 0;
+    const long long total = (long long)rows * (H / 4);
+    embed_add_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float4*>(x), idx, reinterpret_cast<const float4*>(table), reinterpret_cast<float4*>(y),
+        rows, H / 4, n_embed);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_embed_add_bwd(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed,
+                                  void* stream) {
+    TAVK_CHECK(dy && idx && dtable, 1, "tavk_embed_add_bwd: null pointer");
+    TAVK_CHECK(n_embed >= 1 && n_embed <= 8, 2, "tavk_embed_add_bwd: n_embed=%d unsupported (1..8)", n_embed);
+    if (rows <= 0) return 0;
+    const int threads = 128;
+    const int gx = (H + threads - 1) / threads;
+    int chunks = (2 * sm_count() + gx - 1) / gx;
+    int rpc = (rows + chunks - 1) / chunks;
+    if (rpc < 16) rpc = 16;
+    chunks = (rows + rpc - 1) / rpc;
+    embed_add_bwd_kernel<<<dim3(gx, chunks), threads, 0, STREAM(stream)>>>(dy, idx, dtable, rows, H, n_embed, rpc);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H, void* stream) {
+    TAVK_CHECK(x && y, 1, "tavk_mean_pool_fwd: null pointer");
+    TAVK_CHECK(H % 4 == 0, 1, "tavk_mean_pool_fwd: H=%d must be a multiple of 4", H);
+    if (B <= 0) return 0;
+    TAVK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * H * sizeof(float), STREAM(stream)));
+    if (S <= 0) return 0;
+    const int threads = 64;
+    const int gx = (H / 4 + threads - 1) / threads;
+    int chunks = (2 * sm_count() + gx * B - 1) / (gx * B);
+    if (chunks < 1) chunks = 1;
+    int rpc = (S + chunks - 1) / chunks;
+    if (rpc < 8) rpc = 8;
+    chunks = (S + rpc - 1) / rpc;
+    mean_pool_fwd_kernel<<<dim3(gx, chunks, B), threads, 0, STREAM(stream)>>>(reinterpret_cast<const float4*>(x), y, S,
+                                                                            H / 4, rpc, 1.0f / (float)S);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_mean_pool_bwd(const float* dy, float* dx, void* dx_bf16, int B, int S, int H, void* stream) {
+    TAVK_CHECK(dy && (dx || dx_bf16), 1, "tavk_mean_pool_bwd: null pointer");
+    TAVK_CHECK(H % 4 == 0, 1, "tavk_mean_pool_bwd: H=%d must be a multiple of 4", H);
+    if (B <= 0 || S <= 0) return 0;
+    const long long total = (long long)B * S * (H / 4);
+    mean_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), reinterpret_cast<uint2*>(dx_bf16), S, H / 4,
+        total, 1.0f / (float)S);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_colsum(const void* x, int x_dtype, int64_t ld, float* out, int M, int N, int accumulate,
+                           void* stream) {
+    return launch_colsum(x, x_dtype, ld, nullptr, out, 1, M, N, accumulate, STREAM(stream));
+}
+
+extern "C" int tavk_masked_colsum(const void* x, int x_dtype, int64_t ld, const float* w, float* out, int B, int S,
+                                  int N, void* stream) {
+    return launch_colsum(x, x_dtype, ld, w, out, B, S, N, 0, STREAM(stream));
+}
+
+extern "C" int tavk_small_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
+                                     void* stream) {
+    TAVK_CHECK(x && w && y, 1, "tavk_small_linear_fwd: null pointer");
+    if (M <= 0 || N <= 0) return 0;
+    const long long threads_total = (long long)M * N * 32;
+    const int threads = 256;
+    const long long grid = (threads_total + threads - 1) / threads;
+    TAVK_CHECK(grid < (1ll << 31), 2, "tavk_small_linear_fwd: problem too large for this kernel");
+    small_linear_fwd_kernel<<<(int)grid, threads, 0, STREAM(stream)>>>(x, w, b, y, M, N, K);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* dx, int M, int N, int K, int accumulate,
+                                       void* stream) {
+    TAVK_CHECK(dy && w && dx, 1, "tavk_small_linear_bwd_x: null pointer");
+    if (M <= 0 || K <= 0) return 0;
+    const long long total = (long long)M * K;
+    small_linear_bwd_x_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(dy, w, dx, M, N, K, accumulate);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_small_linear_bwd_w(const float* dy, const float* x, float* dw, float* db, int M, int N, int K,
+                                       void* stream) {
+    TAVK_CHECK(dy && x && (dw || db), 1, "tavk_small_linear_bwd_w: null pointer");
+    if (N <= 0 || K <= 0) return 0;
+    const long long total = (long long)N * K;
+    small_linear_bwd_w_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(dy, x, dw, db, M, N, K);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+    TAVK_CHECK(x && y, 1, "tavk_cast_f32_bf16: null pointer");
+    TAVK_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, 1,
+               "tavk_cast_f32_bf16: buffers must be 16/8-byte aligned");
+    if (n <= 0) return 0;
+    cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                                 n);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_scale_f32(const float* x, float* y, float scale, int64_t n, void* stream) {
+    TAVK_CHECK(x && y, 1, "tavk_scale_f32: null pointer");
+    if (n <= 0) return 0;
+    scale_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, y, scale, n);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_dropout(const float* x, float* y, uint8_t* keep_mask, int64_t n, float p, uint64_t seed,
+                            uint64_t offset, void* stream) {
+    TAVK_CHECK(x && y && keep_mask, 1, "tavk_dropout: null pointer");
+    TAVK_CHECK(p >= 0.f && p < 1.f, 1, "tavk_dropout: p=%f out of [0,1)", (double)p);
+    if (n <= 0) return 0;
+    dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, y, keep_mask, n, p, 1.0f / (1.0f - p), seed,
+                                                                     offset);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float* dx, int64_t n, float p,
+                                void* stream) {
+    TAVK_CHECK(dy && dx && keep_mask, 1, "tavk_dropout_bwd: null pointer");
+    if (n <= 0) return 0;
+    dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(dy, keep_mask, dx, n, 1.0f / (1.0f - p));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_permute_bshd_bhds(const void* in, void* out, int B, int S, int nh, int d, int inverse,
+                                      void* stream) {
+    TAVK_CHECK(in && out, 1, "tavk_permute_bshd_bhds: null pointer");
+    if (B <= 0 || S <= 0) return 0;
+    dim3 grid((S + 31) / 32, (d + 31) / 32, B * nh);
+    permute_bshd_bhds_kernel<<<grid, dim3(32, 8), 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                       reinterpret_cast<__nv_bfloat16*>(out), S, nh, d,
+                                                                       inverse);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
