@@ -1,0 +1,508 @@
+"""Transformer-layer engine: forward and backward of a stack of encoder layers executed entirely by libtavk.so kernels.
+
+One ``torch.autograd.Function`` (``EncoderStackFn``) covers every layer family on the TAV path:
+
+  * fusion ``VideoMAELayer`` of the reference (utils/TAVFormer.py:230-271): pre-LN, q/v bias, POST-softmax mask add,
+    handled as unmasked attention plus a rank-1 fp32 term routed through the out-projection;
+  * HF ``VideoMAELayer`` and ``Wav2Vec2EncoderLayerStableLayerNorm``: pre-LN, no mask;
+  * HF ``RobertaLayer`` / ``Wav2Vec2EncoderLayer`` and the reference's custom ``TransformerBlock``
+    (utils/TAVFormer.py:93-142): post-LN, optional pre-softmax key bias, optional scrambled head concat.
+
+Numerics: the residual stream, LayerNorm statistics, biases, the rank-1 term and all parameter gradients are fp32;
+GEMM / attention operands are bf16 with fp32 accumulation (tcgen05 / mma.sync).  Weights stay fp32 ``nn.Parameter``s
+(state_dict compatible); bf16 operand copies ("shadows", QKV packed to [3H,H]) are cached per layer and refreshed when
+a parameter's version counter changes or ``invalidate_shadows()`` is called by the fused optimiser."""
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as L
+
+_generation = 0
+
+
+def invalidate_shadows():
+    """Called after an out-of-band parameter update (fused AdamW through raw pointers)."""
+    global _generation
+    _generation += 1
+
+
+@dataclass(frozen=True)
+class LayerSpec:
+    hidden: int = 768
+    heads: int = 12
+    inter: int = 3072
+    pre_ln: bool = True
+    eps: float = 1e-12
+    mask_mode: str = "none"      # "none" | "key_bias" (pre-softmax additive) | "rank1" (post-softmax additive, Q1)
+    scrambled_concat: bool = False  # reference MultiHeadAttention concat quirk (Q5)
+
+
+# flat parameter order per layer (None allowed for absent biases)
+PARAM_SLOTS = ("ln1_w", "ln1_b", "wq", "wk", "wv", "bq", "bk", "bv", "wo", "bo", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2")
+N_SLOTS = len(PARAM_SLOTS)
+
+
+class LayerShadow:
+    """bf16 operand copies of one layer's matrices + packed fp32 QKV bias."""
+
+    def __init__(self):
+        self.key = None
+        self.wqkv = self.wo = self.w1 = self.w2 = self.bqkv = None
+
+    def refresh(self, p, spec):
+        H = spec.hidden
+        key = (_generation,) + tuple((t.data_ptr(), t._version) if t is not None else None for t in p)
+        if key == self.key:
+            return self
+        dev = p[2].device
+        if self.wqkv is None:
+            self.wqkv = torch.empty((3 * H, H), dtype=torch.bfloat16, device=dev)
+            self.wo = torch.empty((H, H), dtype=torch.bfloat16, device=dev)
+            self.w1 = torch.empty((spec.inter, H), dtype=torch.bfloat16, device=dev)
+            self.w2 = torch.empty((H, spec.inter), dtype=torch.bfloat16, device=dev)
+            self.bqkv = torch.zeros((3 * H,), dtype=torch.float32, device=dev)
+        d = dict(zip(PARAM_SLOTS, p))
+        with torch.no_grad():
+            for i, n in enumerate(("wq", "wk", "wv")):
+                L.cast_bf16(d[n].detach(), self.wqkv[i * H:(i + 1) * H])
+            L.cast_bf16(d["wo"].detach(), self.wo)
+            L.cast_bf16(d["w1"].detach(), self.w1)
+            L.cast_bf16(d["w2"].detach(), self.w2)
+            for i, n in enumerate(("bq", "bk", "bv")):
+                if d[n] is not None:
+                    self.bqkv[i * H:(i + 1) * H].copy_(d[n].detach())
+                else:
+                    self.bqkv[i * H:(i + 1) * H].zero_()
+        self.key = key
+        return self
+
+
+def _wgrad_splits(rows_out, cols_out, k_tokens):
+    tiles = ((rows_out + 127) // 128) * ((cols_out + 255) // 256)
+    sms = 148
+    s = max(1, min(sms // max(tiles, 1), (k_tokens + 511) // 512))
+    return s
+
+
+def _wgrad(dy_bf, x_bf, rows_out, cols_out, tokens):
+    """dW[rows_out, cols_out] = dY^T · X over `tokens` rows; both operands MN-major views of row-major activations."""
+    out = torch.zeros((rows_out, cols_out), dtype=torch.float32, device=dy_bf.device)
+    ks = _wgrad_splits(rows_out, cols_out, tokens)
+    L.gemm(dy_bf, x_bf, out, M=rows_out, N=cols_out, K=tokens, a_mn=True, b_mn=True, accumulate=True, k_splits=ks)
+    return out
+
+
+def _f32(shape, dev):
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
+def _bf16(shape, dev):
+    return torch.empty(shape, dtype=torch.bfloat16, device=dev)
+
+
+class _Saved:
+    __slots__ = ("x", "x_bf", "h1", "mean1", "rstd1", "qkv", "o", "o_used", "lse", "c", "x1", "h2", "mean2", "rstd2",
+                 "pre", "act", "f")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def _attention_fwd(spec, qkv, B, S, key_bias):
+    H, nh = spec.hidden, spec.heads
+    dev = qkv.device
+    o = _bf16((B * S, H), dev)
+    lse = _f32((B, nh, S), dev)
+    L.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, lse, B=B, S=S, nh=nh, ld_qkv=3 * H, ld_o=H,
+               key_bias=key_bias if spec.mask_mode == "key_bias" else None, scale=(H // nh) ** -0.5)
+    return o, lse
+
+
+def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
+    """x: f32 [M,H].  Returns (y_f32, y_bf16 or None, saved)."""
+    H, I = spec.hidden, spec.inter
+    M = B * S
+    dev = x.device
+    d = dict(zip(PARAM_SLOTS, p))
+    sv = _Saved() if keep else None
+    if spec.pre_ln:
+        h1, _, mean1, rstd1 = L.layernorm_fwd(x, d["ln1_w"], d["ln1_b"], spec.eps)
+        qkv = _bf16((M, 3 * H), dev)
+        L.gemm(h1, sh.wqkv, qkv, M=M, N=3 * H, K=H, bias=sh.bqkv)
+        o, lse = _attention_fwd(spec, qkv, B, S, mask2d)
+        rb = c = None
+        if spec.mask_mode == "rank1":
+            # P + m  =>  ctx += sum_k m[b,k] V[b,k,:]  (same vector for every query); keep it fp32 end to end
+            c = _f32((B, H), dev)
+            L.masked_colsum(qkv[:, 2 * H:], mask2d, c, B=B, S=S, N=H, ld=3 * H)
+            rb = _f32((B, H), dev)
+            L.call("tavk_small_linear_fwd", c.data_ptr(), d["wo"].data_ptr(), None, rb.data_ptr(), B, H, H)
+        x1 = _f32((M, H), dev)
+        L.gemm(o, sh.wo, x1, M=M, N=H, K=H, bias=d["bo"], resid=x, rowbias=rb, rows_per_group=S)
+        h2, _, mean2, rstd2 = L.layernorm_fwd(x1, d["ln2_w"], d["ln2_b"], spec.eps)
+        pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
+        L.gemm(h2, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU)
+        y = _f32((M, H), dev)
+        L.gemm(act, sh.w2, y, M=M, N=H, K=I, bias=d["b2"], resid=x1)
+        if keep:
+            sv.x, sv.h1, sv.mean1, sv.rstd1, sv.qkv, sv.o, sv.lse, sv.c = x, h1, mean1, rstd1, qkv, o, lse, c
+            sv.x1, sv.h2, sv.mean2, sv.rstd2, sv.pre, sv.act = x1, h2, mean2, rstd2, pre, act
+        return y, None, sv
+    # post-LN
+    if x_bf is None:
+        x_bf = L.cast_bf16(x)
+    qkv = _bf16((M, 3 * H), dev)
+    L.gemm(x_bf, sh.wqkv, qkv, M=M, N=3 * H, K=H, bias=sh.bqkv)
+    o, lse = _attention_fwd(spec, qkv, B, S, mask2d)
+    o_used = o
+    if spec.scrambled_concat:
+        o_used = _bf16((M, H), dev)
+        L.call("tavk_permute_bshd_bhds", o.data_ptr(), o_used.data_ptr(), B, S, spec.heads, H // spec.heads, 0)
+    a = _f32((M, H), dev)
+    L.gemm(o_used, sh.wo, a, M=M, N=H, K=H, bias=d["bo"], resid=x)
+    y_bf, y_f32, mean1, rstd1 = L.layernorm_fwd(a, d["ln1_w"], d["ln1_b"], spec.eps, want_bf16=True, want_f32=True)
+    pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
+    L.gemm(y_bf, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU)
+    f = _f32((M, H), dev)
+    L.gemm(act, sh.w2, f, M=M, N=H, K=I, bias=d["b2"], resid=y_f32)
+    z_bf, z_f32, mean2, rstd2 = L.layernorm_fwd(f, d["ln2_w"], d["ln2_b"], spec.eps, want_bf16=True, want_f32=True)
+    if keep:
+        sv.x_bf, sv.qkv, sv.o, sv.o_used, sv.lse, sv.x1, sv.mean1, sv.rstd1 = x_bf, qkv, o, o_used, lse, a, mean1, rstd1
+        sv.h2, sv.pre, sv.act, sv.f, sv.mean2, sv.rstd2 = y_bf, pre, act, f, mean2, rstd2
+    return z_f32, z_bf, sv
+
+
+def _attention_bwd(spec, sv, do, B, S, mask2d, dc):
+    H, nh = spec.hidden, spec.heads
+    dev = do.device
+    dqkv = _bf16((B * S, 3 * H), dev)
+    delta = _f32((B, nh, S), dev)
+    qkv = sv.qkv
+    L.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv.o, do, sv.lse, delta, dqkv[:, :H], dqkv[:, H:2 * H],
+               dqkv[:, 2 * H:], B=B, S=S, nh=nh, ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H,
+               key_bias=mask2d if spec.mask_mode == "key_bias" else None,
+               dv_rowscale=mask2d if dc is not None else None, dv_rank1=dc, scale=(H // nh) ** -0.5)
+    return dqkv
+
+
+def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf):
+    """Returns (dx_f32, dx_bf16|None, grads list aligned with PARAM_SLOTS)."""
+    H, I = spec.hidden, spec.inter
+    M = B * S
+    dev = dy.device
+    d = dict(zip(PARAM_SLOTS, p))
+    g = dict.fromkeys(PARAM_SLOTS)
+    zeros = lambda n: torch.zeros((n,), dtype=torch.float32, device=dev)  # noqa: E731
+    if spec.pre_ln:
+        if dy_bf is None:
+            dy_bf = L.cast_bf16(dy)
+        # FFN down
+        g["b2"] = _f32((H,), dev)
+        L.colsum(dy, g["b2"], M=M, N=H)
+        g["w2"] = _wgrad(dy_bf, sv.act, H, I, M)
+        dpre = _bf16((M, I), dev)
+        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD)
+        # FFN up
+        g["b1"] = _f32((I,), dev)
+        L.colsum(dpre, g["b1"], M=M, N=I)
+        g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
+        dh2 = _f32((M, H), dev)
+        L.gemm(dpre, sh.w1, dh2, M=M, N=H, K=I, b_mn=True)
+        g["ln2_w"], g["ln2_b"] = zeros(H), zeros(H)
+        dx1, dx1_bf = L.layernorm_bwd(dh2, sv.x1, sv.mean2, sv.rstd2, d["ln2_w"], g["ln2_w"], g["ln2_b"], resid=dy,
+                                      want_f32=True, want_bf16=True)
+        # attention out-projection
+        g["bo"] = _f32((H,), dev)
+        L.colsum(dx1, g["bo"], M=M, N=H)
+        g["wo"] = _wgrad(dx1_bf, sv.o, H, H, M)
+        dc = None
+        if spec.mask_mode == "rank1":
+            drb = _f32((B, H), dev)
+            L.masked_colsum(dx1, None, drb, B=B, S=S, N=H, ld=H)
+            dc = _f32((B, H), dev)
+            L.call("tavk_small_linear_bwd_x", drb.data_ptr(), d["wo"].data_ptr(), dc.data_ptr(), B, H, H, 0)
+            L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), g["wo"].data_ptr(), None, B, H, H)
+        do = _bf16((M, H), dev)
+        L.gemm(dx1_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
+        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, dc)
+        dbqkv = _f32((3 * H,), dev)
+        L.colsum(dqkv, dbqkv, M=M, N=3 * H)
+        dwqkv = _wgrad(dqkv, sv.h1, 3 * H, H, M)
+        dh1 = _f32((M, H), dev)
+        L.gemm(dqkv, sh.wqkv, dh1, M=M, N=H, K=3 * H, b_mn=True)
+        g["ln1_w"], g["ln1_b"] = zeros(H), zeros(H)
+        dx, dx_bf = L.layernorm_bwd(dh1, sv.x, sv.mean1, sv.rstd1, d["ln1_w"], g["ln1_w"], g["ln1_b"], resid=dx1,
+                                    want_f32=True, want_bf16=need_dx_bf)
+    else:
+        g["ln2_w"], g["ln2_b"] = zeros(H), zeros(H)
+        df, df_bf = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], g["ln2_w"], g["ln2_b"], want_f32=True,
+                                    want_bf16=True)
+        g["b2"] = _f32((H,), dev)
+        L.colsum(df, g["b2"], M=M, N=H)
+        g["w2"] = _wgrad(df_bf, sv.act, H, I, M)
+        dpre = _bf16((M, I), dev)
+        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD)
+        g["b1"] = _f32((I,), dev)
+        L.colsum(dpre, g["b1"], M=M, N=I)
+        g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
+        dyl = _f32((M, H), dev)
+        L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)
+        g["ln1_w"], g["ln1_b"] = zeros(H), zeros(H)
+        da, da_bf = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], g["ln1_w"], g["ln1_b"], want_f32=True,
+                                    want_bf16=True)
+        g["bo"] = _f32((H,), dev)
+        L.colsum(da, g["bo"], M=M, N=H)
+        g["wo"] = _wgrad(da_bf, sv.o_used, H, H, M)
+        do = _bf16((M, H), dev)
+        L.gemm(da_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
+        if spec.scrambled_concat:
+            do2 = _bf16((M, H), dev)
+            L.call("tavk_permute_bshd_bhds", do.data_ptr(), do2.data_ptr(), B, S, spec.heads, H // spec.heads, 1)
+            do = do2
+        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, None)
+        dbqkv = _f32((3 * H,), dev)
+        L.colsum(dqkv, dbqkv, M=M, N=3 * H)
+        dwqkv = _wgrad(dqkv, sv.x_bf, 3 * H, H, M)
+        dx = _f32((M, H), dev)
+        L.gemm(dqkv, sh.wqkv, dx, M=M, N=H, K=3 * H, b_mn=True, resid=da)
+        dx_bf = None
+    for i, (wn, bn) in enumerate((("wq", "bq"), ("wk", "bk"), ("wv", "bv"))):
+        g[wn] = dwqkv[i * H:(i + 1) * H]
+        if d[bn] is not None:
+            g[bn] = dbqkv[i * H:(i + 1) * H]
+    return dx, dx_bf, [g[n] if d[n] is not None else None for n in PARAM_SLOTS]
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """y = layers_n(...layers_1(x)); x f32 [B,S,H]; mask2d f32 [B,S] or None; params = N_SLOTS entries per layer."""
+
+    @staticmethod
+    def forward(ctx, spec, shadows, x, mask2d, *params):
+        L.require_device()
+        B, S, H = x.shape
+        assert H == spec.hidden and x.dtype == torch.float32
+        n_layers = len(params) // N_SLOTS
+        keep = any(ctx.needs_input_grad)  # inference: nothing is saved
+        cur = x.contiguous().view(B * S, H)
+        if mask2d is not None:
+            mask2d = mask2d.contiguous().float()
+        cur_bf = None
+        saved = []
+        for li in range(n_layers):
+            p = params[li * N_SLOTS:(li + 1) * N_SLOTS]
+            sh = shadows[li].refresh(p, spec)
+            cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep)
+            saved.append(sv)
+        ctx.spec, ctx.shadows, ctx.saved, ctx.mask2d, ctx.params, ctx.dims = spec, shadows, saved, mask2d, params, (B, S, H)
+        return cur.view(B, S, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec, B, S, H = ctx.spec, *ctx.dims
+        n_layers = len(ctx.params) // N_SLOTS
+        dy = dy.contiguous().view(B * S, H)
+        if dy.dtype != torch.float32:
+            dy = dy.float()
+        dy_bf = None
+        grads = [None] * len(ctx.params)
+        for li in range(n_layers - 1, -1, -1):
+            p = ctx.params[li * N_SLOTS:(li + 1) * N_SLOTS]
+            dy, dy_bf, g = _layer_bwd(spec, p, ctx.shadows[li], ctx.saved[li], dy, dy_bf, B, S, ctx.mask2d,
+                                      need_dx_bf=(li > 0 and spec.pre_ln))
+            ctx.saved[li] = None  # free activations as we go
+            grads[li * N_SLOTS:(li + 1) * N_SLOTS] = g
+        return (None, None, dy.view(B, S, H), None, *grads)
+
+
+def run_stack(spec, shadows, x, mask2d, layer_params):
+    """layer_params: list (per layer) of N_SLOTS-long lists of tensors/None."""
+    flat = [t for p in layer_params for t in p]
+    return EncoderStackFn.apply(spec, shadows, x, mask2d, *flat)
+
+
+# ------------------------------------------------------------------------------------------------ small fused ops
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        shp = x.shape
+        x2 = x.contiguous().view(-1, shp[-1]).float()
+        _, y, mean, rstd = L.layernorm_fwd(x2, w, b, eps, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.shp = shp
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        H = x2.shape[1]
+        dw = torch.zeros((H,), dtype=torch.float32, device=x2.device)
+        db = torch.zeros((H,), dtype=torch.float32, device=x2.device)
+        dx, _ = L.layernorm_bwd(dy.contiguous().view(-1, H).float(), x2, mean, rstd, w, dw, db)
+        return dx.view(ctx.shp), dw, db, None
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    """nn.LayerNorm over the last dim through tavk_layernorm_{fwd,bwd} (reference models/tav.py:486,488-490)."""
+    return _LayerNormFn.apply(x, w, b, eps)
+
+
+class _MeanPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, S, H = x.shape
+        x = x.contiguous().float()
+        y = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        L.call("tavk_mean_pool_fwd", x.data_ptr(), y.data_ptr(), B, S, H)
+        ctx.dims = (B, S, H)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, S, H = ctx.dims
+        dy = dy.contiguous().float()
+        dx = torch.empty((B, S, H), dtype=torch.float32, device=dy.device)
+        L.call("tavk_mean_pool_bwd", dy.data_ptr(), dx.data_ptr(), None, B, S, H)
+        return dx
+
+
+def mean_pool(x):
+    """torch.mean(x, dim=1) (reference models/tav.py:478,481,488; unmasked — SURVEY Q3)."""
+    return _MeanPoolFn.apply(x)
+
+
+class _EmbedAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, table):
+        B, S, H = x.shape
+        x = x.contiguous().float()
+        idx = idx.contiguous().long()
+        y = torch.empty_like(x)
+        L.call("tavk_embed_add_fwd", x.data_ptr(), idx.data_ptr(), table.data_ptr(), y.data_ptr(), B * S, H, table.shape[0])
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, S, H, table.shape[0])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        B, S, H, n = ctx.dims
+        dt = None
+        if ctx.needs_input_grad[2]:
+            dy = dy.contiguous()
+            dt = torch.zeros((n, H), dtype=torch.float32, device=dy.device)
+            L.call("tavk_embed_add_bwd", dy.data_ptr(), idx.data_ptr(), dt.data_ptr(), B * S, H, n)
+        return dy, None, dt
+
+
+def embed_add(x, idx, table):
+    """x + table[idx] (reference models/tav.py:474)."""
+    return _EmbedAddFn.apply(x, idx, table)
+
+
+class _SmallLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = x.contiguous().float()
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        L.call("tavk_small_linear_fwd", x.data_ptr(), w.data_ptr(), L._ptr(b), y.data_ptr(), M, N, K)
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        M, K = x.shape
+        N = w.shape[0]
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        L.call("tavk_small_linear_bwd_x", dy.data_ptr(), w.data_ptr(), dx.data_ptr(), M, N, K, 0)
+        dw = torch.zeros_like(w)
+        db = torch.zeros((N,), dtype=torch.float32, device=x.device) if ctx.has_b else None
+        L.call("tavk_small_linear_bwd_w", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), L._ptr(db), M, N, K)
+        return dx, dw, db
+
+
+def small_linear(x, w, b=None):
+    """fp32 linear for launch-bound shapes: the classifier head Linear(3072, C) (reference models/tav.py:499)."""
+    return _SmallLinearFn.apply(x, w, b)
+
+
+class _LinearBf16Fn(torch.autograd.Function):
+    """y = x W^T + b with the tcgen05 GEMM (bf16 operands, fp32 accumulate/output): the 1024->768 audio projections
+    (reference models/tav.py:363,478)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        shp = x.shape
+        K, N = shp[-1], w.shape[0]
+        x2 = x.contiguous().view(-1, K)
+        M = x2.shape[0]
+        x_bf = L.cast_bf16(x2.float()) if x2.dtype != torch.bfloat16 else x2
+        w_bf = L.cast_bf16(w.detach())
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        L.gemm(x_bf, w_bf, y, M=M, N=N, K=K, bias=b)
+        ctx.save_for_backward(x_bf, w_bf)
+        ctx.meta = (shp, M, N, K, b is not None)
+        return y.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_bf, w_bf = ctx.saved_tensors
+        shp, M, N, K, has_b = ctx.meta
+        dy2 = dy.contiguous().view(M, N).float()
+        dy_bf = L.cast_bf16(dy2)
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+        L.gemm(dy_bf, w_bf, dx, M=M, N=K, K=N, b_mn=True)
+        dw = _wgrad(dy_bf, x_bf, N, K, M)
+        db = None
+        if has_b:
+            db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+            L.colsum(dy2, db, M=M, N=N)
+        return dx.view(shp), dw, db
+
+
+def linear_bf16(x, w, b=None):
+    return _LinearBf16Fn.apply(x, w, b)
+
+
+class _SoftmaxCEFn(torch.autograd.Function):
+    """Returns (numerator, denominator) of the weighted mean CE so data-parallel ranks can all-reduce the denominator."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight):
+        B, C = logits.shape
+        logits = logits.contiguous().float()
+        target = target.contiguous().long()
+        probs = torch.empty((B, C), dtype=torch.float32, device=logits.device)
+        nd = torch.empty((2,), dtype=torch.float32, device=logits.device)
+        L.call("tavk_softmax_ce_fwd", logits.data_ptr(), target.data_ptr(), L._ptr(weight), probs.data_ptr(),
+               nd.data_ptr(), nd.data_ptr() + 4, B, C)
+        ctx.save_for_backward(probs, target)
+        ctx.weight = weight
+        ctx.mark_non_differentiable(nd[1:])
+        return nd[0], nd[1]
+
+    @staticmethod
+    def backward(ctx, dnum, dden):
+        probs, target = ctx.saved_tensors
+        B, C = probs.shape
+        dl = torch.empty_like(probs)
+        gscale = dnum.contiguous().float().view(1)
+        L.call("tavk_softmax_ce_bwd", probs.data_ptr(), target.data_ptr(), L._ptr(ctx.weight), gscale.data_ptr(),
+               dl.data_ptr(), B, C)
+        return dl, None, None
+
+
+def softmax_ce_parts(logits, target, weight=None):
+    return _SoftmaxCEFn.apply(logits, target, weight)
+
+
+def cross_entropy(logits, target, weight=None):
+    """nn.CrossEntropyLoss(weight=w)(logits, target) with mean reduction (reference utils/global_functions.py:63-64)."""
+    num, den = softmax_ce_parts(logits, target, weight)
+    return num / den
