@@ -470,6 +470,39 @@ def linear_bf16(x, w, b=None):
     return _LinearBf16Fn.apply(x, w, b)
 
 
+_dropout_calls = 0
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, offset):
+        x = x.contiguous().float()
+        y = torch.empty_like(x)
+        keep = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), float(p), int(seed), int(offset))
+        ctx.save_for_backward(keep)
+        ctx.p = float(p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (keep,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(dy)
+        L.call("tavk_dropout_bwd", dy.data_ptr(), keep.data_ptr(), dx.data_ptr(), dy.numel(), ctx.p)
+        return dx, None, None, None
+
+
+def dropout(x, p, seed=None):
+    """nn.Dropout(p) in training mode (the classifier-head dropout, reference models/tav.py:497-498) with a
+    counter-based generator keyed on (torch.initial_seed(), call counter): reproducible, but not torch's stream."""
+    global _dropout_calls
+    if p <= 0.0:
+        return x
+    _dropout_calls += 1
+    return _DropoutFn.apply(x, p, torch.initial_seed() if seed is None else seed, _dropout_calls << 32)
+
+
 class _SoftmaxCEFn(torch.autograd.Function):
     """Returns (numerator, denominator) of the weighted mean CE so data-parallel ranks can all-reduce the denominator."""
 

@@ -1,0 +1,241 @@
+"""Drop-in ``PreFormer`` and ``TAVForMAE`` (reference models/tav.py:249-417 and :420-504) on the sm_100a kernel path.
+
+Constructor arguments, ``forward`` signatures, return values and ``state_dict`` keys are the reference's
+(SURVEY.md §8b).  Differences that are deliberate and documented in DESIGN.md:
+  * everything runs on the module's CUDA device — the reference keeps PreFormer on the CPU and bounces tensors
+    (SURVEY Q11); the ``device=`` argument is still accepted and honoured by moving the module;
+  * the HF sub-models are built from configs when no local checkpoint is available (no network in this image); which
+    sizes are built is chosen with ``set_encoder_variant`` ("reference" = the checkpoints the reference names,
+    "baseline" = the RoBERTa-base / Wav2Vec2-base / VideoMAE-base set BASELINE.json's metric is quoted on);
+  * the audio projection's in-features follow ``wav2vec2.config.hidden_size`` (the reference hard-codes 1024, Q13).
+Quirks that are reproduced on purpose: 12 fusion layers regardless of ``num_layers`` (Q4), plain (unmasked) mean
+pooling (Q3), the wrong-signed additive masks (Q2) that the fusion attention then adds after the softmax (Q1)."""
+import torch
+from torch import nn
+
+from . import engine, hf_adapters as hf
+from .tavformer import VideoMAEEncoder
+
+_VARIANT = "reference"
+_FP16_MIN = torch.finfo(torch.float16).min
+
+
+def set_encoder_variant(name):
+    """"reference" | "baseline" | "tiny" — sizes of the three HF encoders built by the next constructors."""
+    global _VARIANT
+    if name not in ("reference", "baseline", "tiny"):
+        raise ValueError(name)
+    _VARIANT = name
+
+
+def encoder_configs(variant=None):
+    from transformers import RobertaConfig, VideoMAEConfig, Wav2Vec2Config
+
+    variant = variant or _VARIANT
+    w2v = dict(hidden_dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, feat_proj_dropout=0.0,
+               final_dropout=0.0, layerdrop=0.0, apply_spec_augment=False)
+    rob = dict(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1,
+               bos_token_id=0, eos_token_id=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    large = dict(hidden_size=1024, num_attention_heads=16, intermediate_size=4096, feat_extract_norm="layer",
+                 conv_bias=True, do_stable_layer_norm=True)
+    if variant == "reference":   # distilroberta-base (6L) + wav2vec2-large-xlsr (24L) + videomae-base
+        return {"text": RobertaConfig(num_hidden_layers=6, **rob),
+                "audio": Wav2Vec2Config(num_hidden_layers=24, **large, **w2v), "video": VideoMAEConfig()}
+    if variant == "baseline":    # roberta-base + wav2vec2-base + videomae-base
+        return {"text": RobertaConfig(num_hidden_layers=12, **rob), "audio": Wav2Vec2Config(**w2v),
+                "video": VideoMAEConfig()}
+    return {"text": RobertaConfig(num_hidden_layers=2, **rob),
+            "audio": Wav2Vec2Config(num_hidden_layers=2, **large, **w2v), "video": VideoMAEConfig(num_hidden_layers=2)}
+
+
+def _build_encoders():
+    """The reference calls AutoModel.from_pretrained / VideoMAEModel.from_pretrained (models/tav.py:257-263).  There
+    is no network or HF cache here, so the same architectures are instantiated from configs and left in eval mode,
+    which is also the mode from_pretrained returns them in."""
+    from transformers import RobertaModel, VideoMAEModel, Wav2Vec2Model
+
+    c = encoder_configs()
+    return RobertaModel(c["text"]).eval(), Wav2Vec2Model(c["audio"]).eval(), VideoMAEModel(c["video"]).eval()
+
+
+def conv_out_lengths(lengths, conv_kernel, conv_stride):
+    """reference models/tav.py:308-324."""
+    for k, s in zip(conv_kernel, conv_stride):
+        lengths = torch.div(lengths - k, s, rounding_mode="floor") + 1
+    return lengths
+
+
+class PreFormer(nn.Module):
+    """Embeds the three modalities and concatenates them (reference models/tav.py:249-417)."""
+
+    def __init__(self):
+        super().__init__()
+        self.bert, self.wav2vec2, self.videomae = _build_encoders()
+        wh = self.wav2vec2.config.hidden_size
+        self.masked_spec_embed = nn.Parameter(torch.FloatTensor(wh).uniform_())
+        self.wav_2_768 = nn.Linear(wh, 768)
+        self.wav_2_768.weight = torch.nn.init.xavier_normal_(self.wav_2_768.weight)
+        self.check_shapes = 1
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in (self.bert, self.wav2vec2, self.videomae):
+            m.eval()  # the reference never switches the from_pretrained sub-models out of eval mode (Q14)
+        return self
+
+    def _get_feat_extract_output_lengths(self, input_lengths, add_adapter=None):
+        c = self.wav2vec2.config
+        return conv_out_lengths(input_lengths, c.conv_kernel, c.conv_stride)
+
+    def _get_feature_vector_attention_mask(self, feature_vector_length, attention_mask, add_adapter=None):
+        """reference models/tav.py:326-342: frames < f(number of valid samples)."""
+        lengths = self._get_feat_extract_output_lengths(attention_mask.long().sum(-1)).to(torch.long)
+        return torch.arange(feature_vector_length, device=attention_mask.device)[None, :] < lengths[:, None]
+
+    def _mask_hidden_states(self, hidden_states, attention_mask, training=False):
+        """SpecAugment (reference models/tav.py:269-306); active only when train=True and the config enables it."""
+        c = self.wav2vec2.config
+        B, T, H = hidden_states.shape
+        if not getattr(c, "apply_spec_augment", True) or T < c.mask_time_length or not training:
+            return hidden_states
+        from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
+
+        hidden_states = hidden_states.clone()
+        if c.mask_time_prob > 0:
+            idx = _compute_mask_indices((B, T), mask_prob=c.mask_time_prob, mask_length=c.mask_time_length,
+                                        attention_mask=attention_mask.cpu() if attention_mask is not None else None,
+                                        min_masks=c.mask_time_min_masks)
+            idx = torch.tensor(idx, device=hidden_states.device, dtype=torch.bool)
+            hidden_states[idx] = self.masked_spec_embed.to(hidden_states.dtype)
+        if c.mask_feature_prob > 0:
+            idx = _compute_mask_indices((B, H), mask_prob=c.mask_feature_prob, mask_length=c.mask_feature_length,
+                                        min_masks=c.mask_feature_min_masks)
+            idx = torch.tensor(idx, device=hidden_states.device, dtype=torch.bool)
+            hidden_states[idx[:, None].expand(-1, T, -1)] = 0
+        return hidden_states
+
+    def forward(self, input_ids=None, audio_features=None, video_embeds=None, text_mask=None, audio_mask=None,
+                visual_mask=None, device="cpu", train=False):
+        dev = self.wav_2_768.weight.device
+        if device is not None and torch.device(device).type == "cuda" and dev.type != "cuda":
+            self.to(device)
+            dev = self.wav_2_768.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("PreFormer runs on the sm_100a kernel path only: move it to a CUDA device "
+                               "(there is no CPU fallback)")
+        to = lambda t: None if t is None else t.to(dev, non_blocking=True)  # noqa: E731
+        keep_count = None
+        if visual_mask is not None and not visual_mask.is_cuda:
+            keep_count = int(visual_mask[0].sum())  # CPU-side count: avoids a device sync for the token gather
+        input_ids, audio_features, video_embeds = to(input_ids), to(audio_features), to(video_embeds)
+        text_mask, audio_mask, visual_mask = to(text_mask), to(audio_mask), to(visual_mask)
+        # text (models/tav.py:349)
+        if input_ids is not None:
+            embedded_bert = self.bert.embeddings(input_ids=input_ids)
+        # audio (:352-363)
+        feats = self.wav2vec2.feature_extractor(audio_features)
+        if audio_mask is not None:
+            audio_mask = self._get_feature_vector_attention_mask(feats.shape[2], audio_mask, add_adapter=False)
+        embedded_audio, _ = self.wav2vec2.feature_projection(feats.transpose(1, 2))
+        embedded_audio = self._mask_hidden_states(embedded_audio, audio_mask, train)
+        enc = self.wav2vec2.encoder
+        embedded_audio = embedded_audio + enc.pos_conv_embed(embedded_audio)
+        embedded_audio = engine.layer_norm(embedded_audio, enc.layer_norm.weight, enc.layer_norm.bias,
+                                           self.wav2vec2.config.layer_norm_eps)
+        embedded_audio = engine.linear_bf16(embedded_audio, self.wav_2_768.weight, self.wav_2_768.bias)
+        # video (:368): PreFormer keeps the tokens where visual_mask is True
+        embedded_video = hf.video_embeddings(self.videomae.embeddings, video_embeds, ~visual_mask, keep_count)
+        if input_ids is not None:
+            tav = torch.concat((embedded_bert.float(), embedded_audio, embedded_video.float()), dim=1)
+        else:
+            tav = torch.concat((embedded_audio, embedded_video.float()), dim=1)
+        # modality ids and additive masks (:381-411), built on device
+        B, Ta, K = embedded_audio.shape[0], embedded_audio.shape[1], embedded_video.shape[1]
+        parts, masks = [], []
+        if input_ids is not None:
+            T = embedded_bert.shape[1]
+            parts.append(torch.zeros((B, T), dtype=torch.long, device=dev))
+            if text_mask is not None:
+                masks.append((1.0 - text_mask[:, None, None, :].float()) * _FP16_MIN)
+        parts.append(torch.ones((B, Ta), dtype=torch.long, device=dev))
+        if audio_mask is not None:
+            masks.append(1.0 - audio_mask[:, None, None, :].float() * _FP16_MIN)  # reference precedence quirk (Q2)
+        parts.append(torch.full((B, K), 2, dtype=torch.long, device=dev))
+        if visual_mask is not None:
+            masks.append(torch.zeros((B, 1, 1, K), dtype=torch.float32, device=dev))
+        tav_embed = torch.concat(parts, dim=1)
+        attention_mask = torch.concat(masks, dim=-1)
+        if self.check_shapes == 1:
+            self.check_shapes += 1
+        return tav, tav_embed, attention_mask
+
+
+class TAVForMAE(nn.Module):
+    """Fusion classifier (reference models/tav.py:420-504)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.output_dim = args["output_dim"]
+        self.dropout = args["dropout"]
+        self.learn_PosEmbeddings = args["learn_PosEmbeddings"]
+        self.num_layers = args["num_layers"]  # stored and ignored, as in the reference (Q4)
+        self.test_ctr = 1
+        self.train_ctr = 1
+        from transformers import VideoMAEConfig
+
+        self.embedding = nn.Embedding(3, 768)
+        self.embedding.weight.requires_grad = self.learn_PosEmbeddings
+        self.bert, self.wav2vec2, self.videomae = _build_encoders()
+        self.bert_norm = nn.LayerNorm(768)
+        self.random_mae_config = VideoMAEConfig()  # "MCG-NJU/videomae-base" architecture
+        self.random_mae_encoder = VideoMAEEncoder(self.random_mae_config, 12).apply(self.randomize_model)
+        self.rand_norm = nn.LayerNorm(768)
+        self.vid_norm = nn.LayerNorm(768)
+        self.aud_norm = nn.LayerNorm(768)
+        self.dropout = nn.Dropout(self.dropout)
+        self.linear1 = nn.Linear(768 * 4, self.output_dim)
+        self.wav_2_768_2 = nn.Linear(self.wav2vec2.config.hidden_size, 768)
+        self.wav_2_768_2.weight = torch.nn.init.xavier_normal_(self.wav_2_768_2.weight)
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in (self.bert, self.wav2vec2, self.videomae):
+            m.eval()
+        return self
+
+    def randomize_model(self, model):
+        """xavier-uniform matrices, zero biases, unit LayerNorm (reference models/tav.py:461-471)."""
+        for _, m in model.named_modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.xavier_uniform_(m.weight)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.zeros_(m.bias)
+                nn.init.ones_(m.weight)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.zeros_(m.bias)
+        return model
+
+    def forward(self, input_ids, text_attention_mask, audio_features, video_embeds, visual_mask, hidden_states,
+                pos_embed, attention_mask, batch_size=2, check="train"):
+        dev = self.linear1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("TAVForMAE runs on the sm_100a kernel path only: move it to a CUDA device "
+                               "(there is no CPU fallback)")
+        keep_count = None
+        if visual_mask is not None and not visual_mask.is_cuda:
+            keep_count = int((~visual_mask[0]).sum())
+        to = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
+        av = engine.embed_add(to(hidden_states), to(pos_embed), self.embedding.weight)                 # :474
+        aud = hf.run_wav2vec2(self.wav2vec2, to(audio_features))                                        # :476
+        aud = engine.mean_pool(engine.linear_bf16(aud, self.wav_2_768_2.weight, self.wav_2_768_2.bias))  # :478
+        vid = engine.mean_pool(hf.run_videomae(self.videomae, to(video_embeds), to(visual_mask), keep_count))  # :480-481
+        _, t = hf.run_roberta(self.bert, to(input_ids), to(text_attention_mask))                        # :485
+        t = engine.layer_norm(t, self.bert_norm.weight, self.bert_norm.bias, self.bert_norm.eps)        # :486
+        av = self.random_mae_encoder(av, to(attention_mask))                                            # :487
+        av = engine.layer_norm(engine.mean_pool(av), self.rand_norm.weight, self.rand_norm.bias, self.rand_norm.eps)
+        aud = engine.layer_norm(aud, self.aud_norm.weight, self.aud_norm.bias, self.aud_norm.eps)       # :489
+        vid = engine.layer_norm(vid, self.vid_norm.weight, self.vid_norm.bias, self.vid_norm.eps)       # :490
+        tav = torch.cat([av, t, aud, vid], dim=1)                                                       # :495
+        if check == "train":                                                                            # :497-498
+            tav = engine.dropout(tav, self.dropout.p)
+        return engine.small_linear(tav, self.linear1.weight, self.linear1.bias)                         # :499

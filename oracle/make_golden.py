@@ -22,7 +22,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def versions():
     import transformers
 
-    return {"torch": torch.__version__, "transformers": transformers.__version__}
+    return {"torch": str(torch.__version__), "transformers": str(transformers.__version__)}
 
 
 def sub(t):

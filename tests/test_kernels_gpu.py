@@ -135,8 +135,11 @@ def test_attention_fwd_bwd(L, B, S, nh, use_bias):
     L.attn_bwd(q, k, v, o, do, lse, delta, dqkv[..., :H], dqkv[..., H:2 * H], dqkv[..., 2 * H:], B=B, S=S, nh=nh,
                ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H, key_bias=bias, dv_rowscale=rowscale, dv_rank1=rank1)
     unpack = lambda t: t.transpose(1, 2).reshape(B, S, H)  # noqa: E731
-    assert rel_l2(dqkv[..., :H], unpack(qf.grad)) < 1.5e-2
-    assert rel_l2(dqkv[..., H:2 * H], unpack(kf.grad)) < 1.5e-2
+    if S == 1:  # softmax over one key is constant: dQ = dK = 0 exactly; only rounding noise may remain
+        assert dqkv[..., :2 * H].float().abs().max().item() < 1e-6
+    else:
+        assert rel_l2(dqkv[..., :H], unpack(qf.grad)) < 1.5e-2
+        assert rel_l2(dqkv[..., H:2 * H], unpack(kf.grad)) < 1.5e-2
     assert rel_l2(dqkv[..., 2 * H:], unpack(vf.grad) + rowscale[:, :, None] * rank1[:, None, :]) < 1.5e-2
 
 
