@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — TAV training-step throughput on N B200s of one node (contract: see DESIGN.md §Measurement).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5            # our arm (sm_100a kernels, CUDA-graphed step)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W             # one rank per GPU, NCCL
+  python bench.py --impl reference --steps 2 --warmup 1      # the reference's CPU path (oracle port) on host cores
+
+A "step" = one pass of the hot path over one batch: PreFormer + TAVForMAE forward, weighted CE, backward, bucketed
+gradient all-reduce (N>1), clip_grad_norm + AdamW (the `not_grad_accum` body, reference train_model/tav_train.py:56-65)
+on the workload BASELINE.json's metric is quoted on (configs[1]: MELD 7-class, batch 16 per GPU, RoBERTa-base +
+Wav2Vec2-base + VideoMAE-base, random init, synthetic inputs).  Prints ONE JSON line on rank 0."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "TAV fwd+bwd samples/s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="C2")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's, 16 for C2)")
+    ap.add_argument("--variant", default="baseline")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="samples per CPU-baseline step (bounded sample)")
+    return ap.parse_args()
+
+
+def workload_name(cfg, B, variant):
+    from multi_modal_emotion_b200 import synthetic as syn
+
+    c = syn.CONFIGS[cfg]
+    return ("TAV MELD %d-class train step (PreFormer+TAVForMAE fwd, weighted CE, bwd, clip+AdamW), batch %d/GPU, "
+            "T=%d, wav=%d samples, 16x3x224x224 video, fused S=%d, encoders=%s (random init)" % (
+                c["C"], B, c["T"], c["L"], syn.fused_len(cfg), variant))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_run(args, steps, warmup, quiet=False):
+    """The reference's own CPU implementation of the path, restated (oracle port; the reference is Python and
+    the reference tree does not travel to the GPU box), fp32, all host threads, on a bounded sample of the workload."""
+    import torch
+
+    from multi_modal_emotion_b200 import synthetic as syn, tav
+    from oracle import tav_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tav.set_encoder_variant(args.variant)
+    B = args.cpu_batch
+    t0 = time.time()
+    model = tav.TAVForMAE({"output_dim": syn.CONFIGS[args.cfg]["C"], "dropout": 0.4, "learn_PosEmbeddings": True, "num_layers": 12})
+    pre = tav.PreFormer()
+    pre_sd, tav_sd = syn.synth_state_dict(pre, seed=1), syn.synth_state_dict(model, seed=2)
+    del model, pre
+    orc = O.OracleTAV(tav.encoder_configs(args.variant)).load(pre_sd, tav_sd)
+    del pre_sd, tav_sd
+    params = [p for m in list(orc.pre.values()) + list(orc.tav.values()) for p in m.parameters()] + \
+        list(orc.pre_w.values()) + list(orc.tav_w.values())
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+    inputs, labels = syn.make_batch(args.cfg, B=B)
+    w = torch.tensor(syn.MELD_CLASS_WEIGHTS if syn.CONFIGS[args.cfg]["C"] == 7 else [0.5, 0.5])
+    build_s = time.time() - t0
+
+    def step():
+        logits = orc.forward(inputs)
+        loss = O.new_cross_entropy(logits, labels.long(), 1, w, 2)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / max(steps, 1)
+    return {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d-sample batch of the same workload shape, %d timed step(s) after %d warm-up, fp32, torch %s CPU ops, "
+                      "%d threads (model build %.0fs not timed)" % (B, steps, warmup, torch.__version__, cores, build_s),
+            "ms_per_step": dt * 1e3}
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from multi_modal_emotion_b200 import synthetic as syn  # noqa: F401
+
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    r = cpu_reference_run(args, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.cfg, args.cpu_batch, args.variant), "device": "host CPU",
+                       "requested_steps": args.steps, "requested_warmup": args.warmup},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from multi_modal_emotion_b200 import _lib as L, dp, synthetic as syn, tav
+    from multi_modal_emotion_b200.losses import NewCrossEntropyLoss
+    from multi_modal_emotion_b200.optim import FusedAdamW
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.require_device()   # fails loudly when the CUDA extension / an sm_100 device is missing: no fallback
+
+    peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pj = json.load(f)
+        peaks = {"bf16_tflops": pj["bf16_tflops"], "bf16_tflops_sustained": pj.get("bf16_tflops_sustained"),
+                 "hbm_gbs": pj["hbm_gbs"], "source": "measured"}
+    except Exception:  # noqa: BLE001
+        pass
+
+    cfg = args.cfg
+    B = args.batch or syn.CONFIGS[cfg]["B"]
+    C = syn.CONFIGS[cfg]["C"]
+    tav.set_encoder_variant(args.variant)
+    torch.manual_seed(0)
+    model = tav.TAVForMAE({"output_dim": C, "dropout": 0.4, "learn_PosEmbeddings": True, "num_layers": 12})
+    pre = tav.PreFormer()
+    pre.load_state_dict(syn.synth_state_dict(pre, seed=1))
+    model.load_state_dict(syn.synth_state_dict(model, seed=2))
+    model, pre = model.to(dev).train(), pre.to(dev).train()
+    crit = NewCrossEntropyLoss(torch.tensor(syn.MELD_CLASS_WEIGHTS if C == 7 else [0.5, 0.5]), epoch_switch=2)
+    params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
+    opt = FusedAdamW(params, lr=1e-5, weight_decay=1e-4)
+    runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=32, use_cuda_graph=not args.no_graph)
+
+    host_inputs, host_labels = syn.make_batch(cfg, seed=1234 + rank, B=B)
+    host_inputs = [{k: v.pin_memory() for k, v in d.items()} for d in host_inputs]
+    host_labels = host_labels.pin_memory()
+    h2d = sum(v.numel() * v.element_size() for d in host_inputs for v in d.values()) + host_labels.numel() * host_labels.element_size()
+
+    # one eager step first: materialises the flat optimiser buffers / gradient buckets and counts our launches per step
+    k0, c0 = L.kernel_count, L.launch_count
+    L.gemm_log.clear()
+    L.record_gemms = True
+    runner._eager_step(host_inputs, host_labels, 1, "train")
+    L.record_gemms = False
+    torch.cuda.synchronize()
+    kernels_per_step, calls_per_step = L.kernel_count - k0, L.launch_count - c0
+
+    # ---- kernel-only throughput: inputs already resident in HBM
+    dev_inputs = [{k: v.to(dev) for k, v in d.items()} for d in host_inputs]
+    dev_labels = host_labels.to(dev)
+    runner.train_step(dev_inputs, dev_labels, 1, "train")   # builds + captures the graph (its own warm-up inside)
+    if runner.static_inputs() is not None:
+        dev_inputs, dev_labels = runner.static_inputs()      # write-in-place buffers: no copies in the timed region
+    for _ in range(max(args.warmup, 3)):
+        runner.train_step(dev_inputs, dev_labels, 1, "train")
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        loss = runner.train_step(dev_inputs, dev_labels, 1, "train")
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    value = B * world / ms_max * 1e3
+    last_loss = float(loss.item())
+
+    # ---- end to end through the public call with HOST buffers: H2D of the inputs + D2H of the loss every step
+    for _ in range(2):
+        runner.train_step(host_inputs, host_labels, 1, "train").item()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        runner.train_step(host_inputs, host_labels, 1, "train").item()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = t.item()
+
+    line = None
+    if rank == 0:
+        roof, fusion = roofline_and_fusion(torch, L, syn, model, B, cfg, ms_max, peaks)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (tensor-core operands; fp32 accumulate, residual stream, LayerNorm/softmax statistics, optimiser)",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg, B, args.variant), "global_batch": B * world,
+                       "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
+                       "l2_policy": "inputs (%.0f MB/step) and saved activations exceed the 126 MB L2; no explicit flush" % (h2d / 1e6),
+                       "step": "fwd + loss + bwd + grad all-reduce + clip + AdamW"},
+            "e2e": {"value": B * world / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": kernels_per_step * args.steps,
+            "library_calls_per_step": calls_per_step,
+            "clocks": clocks, "roofline": roof, "fusion_block": fusion, "loss": last_loss,
+            "peaks": peaks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args, 1, 1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
+    """Dominant kernel = the tcgen05 GEMM.  Every GEMM launch of one training step was recorded (shape, majors,
+    epilogue) during the eager step; each distinct signature is re-launched back to back on the same stream and timed
+    with CUDA events -> average launch duration per signature; achieved = sum(2MNK) / sum(count x duration)."""
+    import collections
+
+    sigs = collections.Counter(L.gemm_log)
+    total_flops, total_ms = 0.0, 0.0
+    for sig, count in sigs.items():
+        M, N, K, a_mn, b_mn, epi, out_bf16, has_bias, has_resid, has_rb, acc, ks = sig
+        A = torch.randn((K, M) if a_mn else (M, K), device="cuda").bfloat16()
+        Bm = torch.randn((K, N) if b_mn else (N, K), device="cuda").bfloat16()
+        out = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        kw = dict(M=M, N=N, K=K, a_mn=bool(a_mn), b_mn=bool(b_mn), epilogue=epi, accumulate=bool(acc), k_splits=ks)
+        if has_bias:
+            kw["bias"] = torch.zeros(N, device="cuda")
+        if has_resid:
+            kw["resid"] = torch.zeros((M, N), device="cuda")
+        if has_rb:
+            kw["rowbias"], kw["rows_per_group"] = torch.zeros((B, N), device="cuda"), max(1, M // B)
+        if epi == L.EPI_GELU:
+            kw["out2"] = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+        if epi == L.EPI_GELU_BWD:
+            kw["aux"] = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
+        L.record_gemms = False
+        for _ in range(2):
+            L.gemm(A, Bm, out, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            L.gemm(A, Bm, out, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += count * e0.elapsed_time(e1) / reps
+        total_flops += count * 2.0 * M * N * K
+    achieved = total_flops / (total_ms * 1e-3) / 1e12 if total_ms > 0 else 0.0
+    peak = peaks["bf16_tflops"]
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+            "launches_per_step": sum(sigs.values()), "distinct_shapes": len(sigs), "flops_per_step": total_flops,
+            "avg_launch_ms": total_ms / max(1, sum(sigs.values())), "share_of_step": total_ms / step_ms,
+            "method": "each distinct GEMM signature of the step re-launched 10x back to back on the launching stream, CUDA events"}
+    # fusion block alone: 12-layer VideoMAEEncoder fwd+bwd at the workload's fused length, reference-faithful masks
+    S = syn.fused_len(cfg)
+    c = syn.CONFIGS[cfg]
+    Ta = syn.conv_frames(c["L"])
+    enc = model.random_mae_encoder
+    x = torch.randn(B, S, 768, device="cuda", requires_grad=True)
+    mask = syn.reference_masks(B, c["T"], Ta, c["K"], torch.full((B,), c["T"]), torch.full((B,), Ta)).cuda()
+    go = torch.full((B, S, 768), 1.0 / (B * S * 768), device="cuda")
+
+    def fstep():
+        y = enc(x, mask)
+        y.backward(go)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fstep()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fstep()
+    for _ in range(3):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    fms = e0.elapsed_time(e1) / 10
+    fl = 3 * 12 * (14155776 * S + 3072 * S * S) * B
+    fusion = {"ms_fwd_bwd": fms, "tflops": fl / fms / 1e9, "frac_of_bf16_peak": fl / fms / 1e9 / peak, "B": B, "S": S,
+              "flops": fl, "mask_regime": "R (reference PreFormer masks)"}
+    return roof, fusion
+
+
+if __name__ == "__main__":
+    sys.exit(main())

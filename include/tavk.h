@@ -155,9 +155,11 @@ int tavk_small_linear_bwd_w(const float* dy, const float* x, float* dw, float* d
 int tavk_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 /* y = x * scale (f32, in place allowed). */
 int tavk_scale_f32(const float* x, float* y, float scale, int64_t n, void* stream);
-/* y[r, c] = keep[r,c] ? x[r,c]/(1-p) : 0 with a counter-based RNG (seed, offset): head dropout models/tav.py:497-498. */
+/* y[r, c] = keep[r,c] ? x[r,c]/(1-p) : 0 with a counter-based RNG (seed, offset): head dropout models/tav.py:497-498.
+ * offset_dev (optional, device uint64): a step counter added (<<32) to `offset` on the device, so a captured CUDA
+ * graph draws a fresh mask on every replay. */
 int tavk_dropout(const float* x, float* y, uint8_t* keep_mask, int64_t n, float p, uint64_t seed, uint64_t offset,
-                 void* stream);
+                 const uint64_t* offset_dev, void* stream);
 int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float* dx, int64_t n, float p, void* stream);
 /* bf16 [B,S,nh,d] -> [B,nh,d,S] (inverse=0) or back (inverse=1): the reference MultiHeadAttention "concat" reinterprets
  * a [B,nh,d,S] buffer as [B,S,nh*d] (utils/TAVFormer.py:86); backward uses the inverse permutation. */

@@ -81,7 +81,7 @@ SIGNATURES = {
     "tavk_small_linear_bwd_w": [_P, _P, _P, _P, _I, _I, _I, _P],
     "tavk_cast_f32_bf16": [_P, _P, _L, _P],
     "tavk_scale_f32": [_P, _P, _F, _L, _P],
-    "tavk_dropout": [_P, _P, _P, _L, _F, _U64, _U64, _P],
+    "tavk_dropout": [_P, _P, _P, _L, _F, _U64, _U64, _P, _P],
     "tavk_dropout_bwd": [_P, _P, _P, _L, _F, _P],
     "tavk_permute_bshd_bhds": [_P, _P, _I, _I, _I, _I, _I, _P],
     "tavk_softmax_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
@@ -92,7 +92,12 @@ SIGNATURES = {
 _RESTYPES = {"tavk_last_error": C.c_char_p}
 
 _lib = None
-launch_count = 0  # kernels-library entry points invoked (bench.py reports it as gpu_launches evidence)
+launch_count = 0   # library entry points invoked
+kernel_count = 0   # CUDA kernels those entry points launched (bench.py reports it as gpu_launches)
+record_gemms = False
+gemm_log = []      # (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, rowbias, accumulate, k_splits) per launch
+# kernels launched per entry point (memset nodes are not counted)
+_KERNELS = {"tavk_attn_bwd": 3}
 
 
 def lib():
@@ -127,10 +132,12 @@ def _stream():
 
 def call(name, *args):
     """Invoke an entry point on torch's current stream (appended as the last argument)."""
-    global launch_count
+    global launch_count, kernel_count
     launch_count += 1
-    rc = getattr(lib(), name)(*args, _stream())
-    _check(rc, name)
+    kernel_count += _KERNELS.get(name, 1)
+    rc = getattr(lib(), name)(*args, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        _check(rc, name)
 
 
 def require_device():
@@ -154,6 +161,9 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.rowbias, a.rows_per_group = _ptr(rowbias), rows_per_group
     a.aux, a.ldaux = _ptr(aux), (aux.stride(0) if aux is not None else 0)
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
+    if record_gemms:
+        gemm_log.append((M, N, K, int(a_mn), int(b_mn), epilogue, int(out.dtype == torch.bfloat16), int(bias is not None),
+                         int(resid is not None), int(rowbias is not None), int(accumulate), k_splits))
     call("tavk_gemm_bf16", C.byref(a))
 
 

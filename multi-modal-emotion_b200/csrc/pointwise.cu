@@ -207,7 +207,9 @@ TAVK_DEVINL float uniform01(uint64_t seed, uint64_t ctr) {
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ keep,
-                                   long long n, float p, float inv_keep, uint64_t seed, uint64_t offset) {
+                                   long long n, float p, float inv_keep, uint64_t seed, uint64_t offset,
+                                   const uint64_t* __restrict__ offset_dev) {
+    if (offset_dev != nullptr) offset += (*offset_dev) << 32;  // device-side step counter (CUDA-graph replays)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
         const bool k = uniform01(seed, offset + (uint64_t)i) >= p;
@@ -390,12 +392,12 @@ extern "C" int tavk_scale_f32(const float* x, float* y, float scale, int64_t n, 
 }
 
 extern "C" int tavk_dropout(const float* x, float* y, uint8_t* keep_mask, int64_t n, float p, uint64_t seed,
-                            uint64_t offset, void* stream) {
+                            uint64_t offset, const uint64_t* offset_dev, void* stream) {
     TAVK_CHECK(x && y && keep_mask, 1, "tavk_dropout: null pointer");
     TAVK_CHECK(p >= 0.f && p < 1.f, 1, "tavk_dropout: p=%f out of [0,1)", (double)p);
     if (n <= 0) return 0;
     dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, y, keep_mask, n, p, 1.0f / (1.0f - p), seed,
-                                                                     offset);
+                                                                     offset, offset_dev);
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,211 @@
+"""Data-parallel execution of the TAV step: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+
+The reference has no distributed code at all — the batch shards trivially because every op on the
+path is per-sample (§8e).  Ranks couple through exactly three quantities, each handled so that N ranks reproduce the
+single-process step on the concatenated batch:
+  1. parameter gradients  -> bucketed all-reduce(SUM) of contiguous ranges of the flat gradient buffer
+     (optim.FlatParams), launched from post-accumulate-grad hooks on a side stream while backward is still running;
+  2. the (weighted) CE normaliser sum_i w[y_i] -> one scalar all-reduce in the forward pass; every rank then
+     back-propagates  num_local / den_global  so the summed gradients are the gradients of the global loss;
+  3. clip_grad_norm_ -> computed after the reduction, when every rank holds the same gradient: no extra collective.
+The bucket plumbing is device-agnostic (it is exercised on CPU with gloo, world_size 2, in tests/test_dp_cpu.py)."""
+import torch
+import torch.distributed as dist
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def global_loss(num, den, group=None):
+    """(loss to back-propagate on this rank, global loss value).  Gradients must then be SUM-reduced."""
+    if not is_distributed():
+        return num / den, (num / den).detach()
+    den_g = den.detach().clone()
+    dist.all_reduce(den_g, op=dist.ReduceOp.SUM, group=group)
+    num_g = num.detach().clone()
+    dist.all_reduce(num_g, op=dist.ReduceOp.SUM, group=group)
+    return num / den_g, num_g / den_g
+
+
+class GradBuckets:
+    """Splits a flat gradient buffer into parameter-aligned buckets and all-reduces each one as soon as every
+    parameter in it has accumulated its gradient."""
+
+    def __init__(self, flat, bucket_bytes=32 << 20, group=None):
+        self.flat, self.group = flat, group
+        self.buckets = []   # (start, end, n_params)
+        self.param_bucket = {}
+        cap = max(1, bucket_bytes // 4)
+        # backward produces gradients roughly in reverse registration order: build buckets from the tail
+        ends = [o + p.numel() for p, o in zip(flat.params, flat.offsets)]
+        i = len(flat.params) - 1
+        while i >= 0:
+            end = flat.numel if not self.buckets else self.buckets[-1][0]
+            j = i
+            while j > 0 and end - flat.offsets[j - 1] <= cap:
+                j -= 1
+            start = flat.offsets[j]
+            self.buckets.append((start, end, i - j + 1))
+            for k in range(j, i + 1):
+                self.param_bucket[id(flat.params[k])] = len(self.buckets) - 1
+            i = j - 1
+        del ends
+        self.pending = [0] * len(self.buckets)
+        self.works = []
+        self.enabled = False
+        self.cuda = flat.grad.is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in flat.params]
+        self.launched = 0
+
+    def start_backward(self):
+        """Arm the buckets for one backward pass."""
+        self.pending = [n for (_, _, n) in self.buckets]
+        self.works = []
+        self.enabled = True
+        self.launched = 0
+
+    def _launch(self, b):
+        s, e, _ = self.buckets[b]
+        view = self.flat.grad[s:e]
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.launched += 1
+
+    def _hook(self, p):
+        if not self.enabled:
+            return
+        b = self.param_bucket[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        """Reduce whatever did not fire from a hook (parameters without a gradient this step) and wait."""
+        if self.enabled:
+            for b, n in enumerate(self.pending):
+                if n > 0:
+                    self.pending[b] = 0
+                    self._launch(b)
+        for w in self.works:
+            w.wait()
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.works = []
+        self.enabled = False
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
+class DataParallelTAV:
+    """Drives one data-parallel training step of (PreFormer, TAVForMAE): forward on the local shard, global-loss
+    normalisation, backward overlapped with bucketed gradient all-reduce, fused clip + AdamW on identical gradients."""
+
+    def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=32, group=None,
+                 use_cuda_graph=False, graph_warmup=3):
+        self.model, self.pre, self.criterion, self.opt = model, PREFormer, criterion, optimizer
+        self.clip, self.group, self.bucket_bytes = clip, group, bucket_mb << 20
+        self.buckets = None
+        self.use_cuda_graph, self.graph_warmup = use_cuda_graph, graph_warmup
+        self._graph = None
+        self.world = dist.get_world_size(group) if is_distributed() else 1
+        if self.world > 1:
+            # replicas must start identical: broadcast rank 0's parameters and buffers
+            for m in (model, PREFormer):
+                for t in list(m.parameters()) + list(m.buffers()):
+                    dist.broadcast(t.data, src=0, group=group)
+            optimizer.on_materialize = self._on_materialize
+
+    def _on_materialize(self, flat):
+        self.buckets = GradBuckets(flat, self.bucket_bytes, self.group)
+
+    # -- CUDA-graph path: the whole step (forward, loss, backward, bucketed all-reduce, clip + AdamW) is captured
+    #    once per (shape, epoch-parity, check) and replayed; per step the host only enqueues the input copies and
+    #    one graph launch.  Inputs may live on the host (pinned or pageable) or already on the device.
+    def _graph_key(self, inputs, labels, epoch, check):
+        shapes = tuple((k, tuple(v.shape), v.dtype) for d in inputs for k, v in d.items())
+        weighted = getattr(self.criterion, "epoch_switch", None)
+        return (shapes, tuple(labels.shape), check, (epoch % weighted) if weighted else 0)
+
+    def _build_graph(self, inputs, labels, epoch, check):
+        dev = next(self.model.parameters()).device
+        st_in = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in d.items()} for d in inputs]
+        st_lab = torch.empty(labels.shape, dtype=labels.dtype, device=dev)
+        # host-side facts the modules need without a device sync (token count kept by the video mask)
+        self.pre.static_keep_count = int(inputs[2]["attention_mask"][0].sum())
+        self.model.static_keep_count = int((~inputs[2]["attention_mask"][0]).sum())
+
+        def load():
+            for d, sd in zip(inputs, st_in):
+                for k, v in d.items():
+                    sd[k].copy_(v, non_blocking=True)
+            st_lab.copy_(labels, non_blocking=True)
+
+        load()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.graph_warmup):
+                self._eager_step(st_in, st_lab, epoch, check)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._eager_step(st_in, st_lab, epoch, check)
+        return {"graph": g, "inputs": st_in, "labels": st_lab, "loss": out}
+
+    def train_step(self, inputs, labels, epoch=1, check="train"):
+        """One optimisation step on this rank's shard.  Returns the GLOBAL loss as a device scalar."""
+        if not self.use_cuda_graph:
+            return self._eager_step(inputs, labels, epoch, check)
+        key = self._graph_key(inputs, labels, epoch, check)
+        if self._graph is None or self._graph["key"] != key:
+            self._graph = self._build_graph(inputs, labels, epoch, check)
+            self._graph["key"] = key
+        st = self._graph
+        for d, sd in zip(inputs, st["inputs"]):
+            for k, v in d.items():
+                if sd[k].data_ptr() != v.data_ptr():
+                    sd[k].copy_(v, non_blocking=True)
+        if st["labels"].data_ptr() != labels.data_ptr():
+            st["labels"].copy_(labels, non_blocking=True)
+        st["graph"].replay()
+        return st["loss"]
+
+    def static_inputs(self):
+        """Device-resident input buffers of the captured step (write into them to skip the host copy)."""
+        return (self._graph["inputs"], self._graph["labels"]) if self._graph else None
+
+    def _eager_step(self, inputs, labels, epoch=1, check="train"):
+        from .tav_train import get_statistics  # local import: tav_train imports optim, not dp
+
+        crit = self.criterion
+        holder = {}
+
+        def parts_criterion(output, label, epoch=None):
+            num, den = crit.parts(output, label, epoch)
+            loss_bwd, loss_val = global_loss(num, den, self.group)
+            holder["value"] = loss_val
+            return loss_bwd
+
+        if self.buckets is not None:
+            self.buckets.start_backward()
+        loss = get_statistics(inputs, labels, self.model, self.pre, parts_criterion, None, check=check, epoch=epoch)
+        loss.backward()
+        if self.world > 1:
+            if self.buckets is not None:
+                self.buckets.finish()
+            else:
+                # first step: the flat buffer does not exist yet -> flatten now, reduce it in one piece
+                self.opt.materialize()
+                self.opt.flat.attach_grads()
+                dist.all_reduce(self.opt.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.opt.step(max_grad_norm=self.clip)
+        return holder["value"]

@@ -470,16 +470,18 @@ def linear_bf16(x, w, b=None):
     return _LinearBf16Fn.apply(x, w, b)
 
 
-_dropout_calls = 0
+_dropout_counter = {}
 
 
 class _DropoutFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, p, seed, offset):
+    def forward(ctx, x, p, seed, counter):
         x = x.contiguous().float()
         y = torch.empty_like(x)
         keep = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-        L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), float(p), int(seed), int(offset))
+        L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), float(p), int(seed), 0,
+               counter.data_ptr())
+        counter.add_(1)  # device-side: also advances on every CUDA-graph replay
         ctx.save_for_backward(keep)
         ctx.p = float(p)
         return y
@@ -495,12 +497,19 @@ class _DropoutFn(torch.autograd.Function):
 
 def dropout(x, p, seed=None):
     """nn.Dropout(p) in training mode (the classifier-head dropout, reference models/tav.py:497-498) with a
-    counter-based generator keyed on (torch.initial_seed(), call counter): reproducible, but not torch's stream."""
-    global _dropout_calls
+    counter-based generator keyed on (torch.initial_seed(), device-side call counter): reproducible after
+    torch.manual_seed + reset_dropout_counter(), but not torch's own random stream."""
     if p <= 0.0:
         return x
-    _dropout_calls += 1
-    return _DropoutFn.apply(x, p, torch.initial_seed() if seed is None else seed, _dropout_calls << 32)
+    c = _dropout_counter.get(x.device)
+    if c is None:
+        c = _dropout_counter[x.device] = torch.zeros(1, dtype=torch.int64, device=x.device)
+    return _DropoutFn.apply(x, p, (torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF, c)
+
+
+def reset_dropout_counter():
+    for c in _dropout_counter.values():
+        c.zero_()
 
 
 class _SoftmaxCEFn(torch.autograd.Function):

@@ -124,7 +124,7 @@ class PreFormer(nn.Module):
             raise RuntimeError("PreFormer runs on the sm_100a kernel path only: move it to a CUDA device "
                                "(there is no CPU fallback)")
         to = lambda t: None if t is None else t.to(dev, non_blocking=True)  # noqa: E731
-        keep_count = None
+        keep_count = getattr(self, "static_keep_count", None)
         if visual_mask is not None and not visual_mask.is_cuda:
             keep_count = int(visual_mask[0].sum())  # CPU-side count: avoids a device sync for the token gather
         input_ids, audio_features, video_embeds = to(input_ids), to(audio_features), to(video_embeds)
@@ -221,7 +221,7 @@ class TAVForMAE(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("TAVForMAE runs on the sm_100a kernel path only: move it to a CUDA device "
                                "(there is no CPU fallback)")
-        keep_count = None
+        keep_count = getattr(self, "static_keep_count", None)
         if visual_mask is not None and not visual_mask.is_cuda:
             keep_count = int((~visual_mask[0]).sum())
         to = lambda t: t.to(dev, non_blocking=True)  # noqa: E731

@@ -55,6 +55,8 @@ def get_statistics(input, label, model, PREFormer, criterion, Metric, check="tra
                    visual_mask=vid_mask if keep is not None else vid_mask_d, hidden_states=tav, pos_embed=tav_embed,
                    attention_mask=attention_mask, batch_size=batch_size, check=check)
     label = label.to(device, **nb).long()
+    if label.dim() > 1:
+        label = label.view(-1)
     if Metric is not None:
         Metric.update_metrics(torch.argmax(output, dim=1), label)
     batch_loss = None

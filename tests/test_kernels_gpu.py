@@ -248,13 +248,16 @@ def test_cast_scale_dropout_permute(L):
     L.call("tavk_scale_f32", x.data_ptr(), y.data_ptr(), 0.25, x.numel())
     assert torch.equal(y, x * 0.25)
     keep = torch.empty(x.numel(), device="cuda", dtype=torch.uint8)
-    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), 0.4, 1234, 0)
+    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), 0.4, 1234, 0, None)
     frac = keep.float().mean().item()
     assert abs(frac - 0.6) < 0.01
     assert torch.allclose(y, torch.where(keep.bool(), x / 0.6, torch.zeros_like(x)), rtol=1e-6, atol=0)
     keep2 = torch.empty_like(keep)
-    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep2.data_ptr(), x.numel(), 0.4, 1234, 0)
+    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep2.data_ptr(), x.numel(), 0.4, 1234, 0, None)
     assert torch.equal(keep, keep2)  # counter-based: reproducible for (seed, offset)
+    ctr = torch.ones(1, dtype=torch.int64, device="cuda")
+    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep2.data_ptr(), x.numel(), 0.4, 1234, 0, ctr.data_ptr())
+    assert not torch.equal(keep, keep2)  # device-side step counter changes the stream (CUDA-graph replays)
     dx = torch.empty_like(x)
     L.call("tavk_dropout_bwd", y.data_ptr(), keep.data_ptr(), dx.data_ptr(), x.numel(), 0.4)
     assert torch.allclose(dx, torch.where(keep.bool(), y / 0.6, torch.zeros_like(y)), rtol=1e-6, atol=0)
