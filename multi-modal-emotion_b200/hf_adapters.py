@@ -55,7 +55,10 @@ def video_embeddings(emb, pixel_values, bool_masked_pos, keep_count=None):
     keep the rows where ``~bool_masked_pos``.  Every row keeps the same number of tokens (HF requirement),
     so the boolean gather is done with a stable sort + take instead of a host-synchronising nonzero()."""
     x = emb.patch_embeddings(pixel_values)
-    x = x + emb.position_embeddings.detach().type_as(x).to(device=x.device)
+    pos = getattr(emb, "_tavk_pos", None)   # HF keeps the sinusoid table as a plain CPU tensor: cache a device copy
+    if pos is None or pos.device != x.device or pos.dtype != x.dtype:
+        pos = emb._tavk_pos = emb.position_embeddings.detach().to(device=x.device, dtype=x.dtype)
+    x = x + pos
     if bool_masked_pos is None:
         return x
     keep = ~bool_masked_pos.to(x.device)
