@@ -91,17 +91,29 @@ __global__ void colsum_kernel(const void* __restrict__ x_, long long ld, const f
     const int s1 = min(s0 + rows_per_chunk, S);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* wb = w ? w + (size_t)b * S : nullptr;
-    for (int s = s0; s < s1; ++s) {
-        const float ws = wb ? wb[s] : 1.0f;
-        float4 v;
+    auto load = [&](int s) -> float4 {
         if (BF16) {
             const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x_) +
                                                            ((size_t)b * S + s) * ld + c4 * 4);
             const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
-            v = make_float4(a.x, a.y, c.x, c.y);
-        } else {
-            v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + ((size_t)b * S + s) * ld + c4 * 4);
+            return make_float4(a.x, a.y, c.x, c.y);
         }
+        return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x_) + ((size_t)b * S + s) * ld + c4 * 4);
+    };
+    int s = s0;
+    for (; s + 4 <= s1; s += 4) {   // four independent row loads in flight
+        float4 v[4];
+        float ws[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = load(s + j); ws[j] = wb ? wb[s + j] : 1.0f; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc.x += ws[j] * v[j].x; acc.y += ws[j] * v[j].y; acc.z += ws[j] * v[j].z; acc.w += ws[j] * v[j].w;
+        }
+    }
+    for (; s < s1; ++s) {
+        const float4 v = load(s);
+        const float ws = wb ? wb[s] : 1.0f;
         acc.x += ws * v.x; acc.y += ws * v.y; acc.z += ws * v.z; acc.w += ws * v.w;
     }
     float* o = out + (size_t)b * N + c4 * 4;
@@ -157,15 +169,26 @@ __global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float
     s = warp_sum(s);
     if (lane == 0) y[o] = s + (b ? b[n] : 0.f);
 }
-// dx[m,k] (+)= sum_n dy[m,n] w[n,k]; one thread per (m,k)
+// dx[m,k] (+)= sum_n dy[m,n] w[n,k]; one thread per (m,k) and per chunk of n (blockIdx.y), 8 loads in flight,
+// partial sums combined with one atomic per thread (dx is zeroed by the host wrapper unless accumulating)
 __global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                          float* __restrict__ dx, int M, int N, int K, int accumulate) {
+                                          float* __restrict__ dx, int M, int N, int K, int n_per_chunk) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)M * K) return;
     const int m = (int)(i / K), k = (int)(i - (long long)m * K);
+    const int n0 = blockIdx.y * n_per_chunk, n1 = min(n0 + n_per_chunk, N);
+    const float* dyr = dy + (size_t)m * N;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s += dy[(size_t)m * N + n] * __ldg(w + (size_t)n * K + k);
-    dx[i] = accumulate ? dx[i] + s : s;
+    int n = n0;
+    for (; n + 8 <= n1; n += 8) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = __ldg(w + (size_t)(n + j) * K + k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += dyr[n + j] * a[j];
+    }
+    for (; n < n1; ++n) s += dyr[n] * __ldg(w + (size_t)n * K + k);
+    atomicAdd(dx + i, s);
 }
 // dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n,k)
 __global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x,
@@ -357,7 +380,14 @@ extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* d
     TAVK_CHECK(dy && w && dx, 1, "tavk_small_linear_bwd_x: null pointer");
     if (M <= 0 || K <= 0) return 0;
     const long long total = (long long)M * K;
-    small_linear_bwd_x_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(dy, w, dx, M, N, K, accumulate);
+    if (!accumulate) TAVK_CUDA(cudaMemsetAsync(dx, 0, (size_t)total * sizeof(float), STREAM(stream)));
+    const int gx = (int)((total + 127) / 128);
+    int chunks = (2 * sm_count() + gx - 1) / gx;
+    if (chunks < 1) chunks = 1;
+    int npc = (N + chunks - 1) / chunks;
+    if (npc < 8) npc = 8;
+    chunks = (N + npc - 1) / npc;
+    small_linear_bwd_x_kernel<<<dim3(gx, chunks), 128, 0, STREAM(stream)>>>(dy, w, dx, M, N, K, npc);
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

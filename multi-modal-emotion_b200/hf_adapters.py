@@ -8,7 +8,7 @@ positional conv, patch-embedding conv, token/position embeddings) still execute 
 lists them as the "next" rows.  Layer families and their LayerNorm placement follow SURVEY.md Appendix A."""
 import torch
 
-from . import engine
+from . import engine, frontends
 from .engine import LayerSpec
 
 
@@ -51,22 +51,9 @@ def run_videomae(model, pixel_values, bool_masked_pos=None, keep_count=None):
 
 
 def video_embeddings(emb, pixel_values, bool_masked_pos, keep_count=None):
-    """VideoMAEEmbeddings.forward: Conv3d patch projection (kernel = stride = (2,16,16)) + fixed sinusoid table, then
-    keep the rows where ``~bool_masked_pos``.  Every row keeps the same number of tokens (HF requirement),
-    so the boolean gather is done with a stable sort + take instead of a host-synchronising nonzero()."""
-    x = emb.patch_embeddings(pixel_values)
-    pos = getattr(emb, "_tavk_pos", None)   # HF keeps the sinusoid table as a plain CPU tensor: cache a device copy
-    if pos is None or pos.device != x.device or pos.dtype != x.dtype:
-        pos = emb._tavk_pos = emb.position_embeddings.detach().to(device=x.device, dtype=x.dtype)
-    x = x + pos
-    if bool_masked_pos is None:
-        return x
-    keep = ~bool_masked_pos.to(x.device)
-    if keep_count is None:
-        keep_count = int(keep[0].sum().item())
-    # stable descending sort of the keep flags lists kept positions first, in their original order
-    idx = torch.sort(keep.to(torch.uint8), dim=1, descending=True, stable=True).indices[:, :keep_count]
-    return torch.gather(x, 1, idx[:, :, None].expand(-1, -1, x.shape[-1]))
+    """VideoMAEEmbeddings.forward on the tcgen05 GEMM (frontends.video_embeddings): gather the kept tokens first,
+    project, add the sinusoid rows in the epilogue."""
+    return frontends.video_embeddings(emb, pixel_values, bool_masked_pos, keep_count)
 
 
 # ------------------------------------------------------------------------------------------------ RoBERTa
@@ -111,7 +98,7 @@ def wav2vec2_layer_slots(lyr):
 
 def wav2vec2_front(model, wav):
     """feature_extractor (7 x Conv1d) -> transpose -> feature_projection (LN + Linear): [B,L] -> [B,Ta,H]."""
-    feats = model.feature_extractor(wav).transpose(1, 2)
+    feats = frontends.feature_extractor(model, wav).transpose(1, 2)
     hidden, _ = model.feature_projection(feats)
     return hidden
 
@@ -122,7 +109,7 @@ def wav2vec2_encoder(model, hidden):
     c = model.config
     _check_head_dim(c.hidden_size, c.num_attention_heads)
     enc = model.encoder
-    hidden = hidden + enc.pos_conv_embed(hidden)
+    hidden = hidden + frontends.pos_conv_embed(enc.pos_conv_embed, hidden)
     stable = bool(c.do_stable_layer_norm)
     if not stable:
         hidden = engine.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, c.layer_norm_eps)

@@ -13,7 +13,7 @@ pooling (Q3), the wrong-signed additive masks (Q2) that the fusion attention the
 import torch
 from torch import nn
 
-from . import engine, hf_adapters as hf
+from . import engine, frontends, hf_adapters as hf
 from .tavformer import VideoMAEEncoder
 
 _VARIANT = "reference"
@@ -133,13 +133,13 @@ class PreFormer(nn.Module):
         if input_ids is not None:
             embedded_bert = self.bert.embeddings(input_ids=input_ids)
         # audio (:352-363)
-        feats = self.wav2vec2.feature_extractor(audio_features)
+        feats = frontends.feature_extractor(self.wav2vec2, audio_features)
         if audio_mask is not None:
             audio_mask = self._get_feature_vector_attention_mask(feats.shape[2], audio_mask, add_adapter=False)
         embedded_audio, _ = self.wav2vec2.feature_projection(feats.transpose(1, 2))
         embedded_audio = self._mask_hidden_states(embedded_audio, audio_mask, train)
         enc = self.wav2vec2.encoder
-        embedded_audio = embedded_audio + enc.pos_conv_embed(embedded_audio)
+        embedded_audio = embedded_audio + frontends.pos_conv_embed(enc.pos_conv_embed, embedded_audio)
         embedded_audio = engine.layer_norm(embedded_audio, enc.layer_norm.weight, enc.layer_norm.bias,
                                            self.wav2vec2.config.layer_norm_eps)
         embedded_audio = engine.linear_bf16(embedded_audio, self.wav_2_768.weight, self.wav_2_768.bias)

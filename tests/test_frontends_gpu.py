@@ -1,0 +1,70 @@
+"""GPU parity of the GEMM-based front-ends (multi_modal_emotion_b200.frontends) against the HF / torch modules they
+replace: VideoMAE patch embedding (Conv3d) with token drop, and the Wav2Vec2 grouped positional convolution with
+weight-norm, forward and backward.  Tolerance: bf16 operands, fp32 accumulation -> 1e-2 relative-L2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("masked", [True, False])
+def test_patch_embedding_matches_hf(masked):
+    from transformers import VideoMAEConfig, VideoMAEModel
+
+    from multi_modal_emotion_b200 import frontends, synthetic as syn
+
+    m = VideoMAEModel(VideoMAEConfig(num_hidden_layers=1)).cuda()
+    m.load_state_dict({k: v.cuda() for k, v in syn.synth_state_dict(m, seed=4).items()})
+    g = torch.Generator().manual_seed(0)
+    B, K = 3, 104
+    video = torch.randn(B, 16, 3, 224, 224, generator=g).cuda()
+    mask = None
+    if masked:
+        mask = torch.zeros(B, 1568, dtype=torch.bool)
+        for b in range(B):
+            mask[b, torch.randperm(1568, generator=g)[:1568 - K]] = True   # masked positions are dropped
+        mask = mask.cuda()
+    ref = m.embeddings(video, mask)
+    probe = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    (ref * probe).sum().backward()
+    gw, gb = m.embeddings.patch_embeddings.projection.weight.grad.clone(), m.embeddings.patch_embeddings.projection.bias.grad.clone()
+    m.zero_grad()
+    out = frontends.video_embeddings(m.embeddings, video, mask)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 1e-2
+    (out * probe).sum().backward()
+    assert rel(m.embeddings.patch_embeddings.projection.weight.grad, gw) < 1e-2
+    assert rel(m.embeddings.patch_embeddings.projection.bias.grad, gb) < 1e-3
+
+
+@pytest.mark.parametrize("hidden,T", [(768, 149), (1024, 49), (768, 1)])
+def test_positional_conv_matches_hf(hidden, T):
+    from transformers import Wav2Vec2Config
+    from transformers.models.wav2vec2.modeling_wav2vec2 import Wav2Vec2PositionalConvEmbedding
+
+    from multi_modal_emotion_b200 import frontends
+
+    torch.manual_seed(0)
+    pc = Wav2Vec2PositionalConvEmbedding(Wav2Vec2Config(hidden_size=hidden)).cuda()
+    with torch.no_grad():
+        pc.conv.bias.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4, T, hidden, generator=g).cuda()
+    probe = torch.randn(4, T, hidden, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = pc(xr)
+    (ref * probe).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in pc.named_parameters()}
+    pc.zero_grad()
+    xo = x.clone().requires_grad_(True)
+    out = frontends.pos_conv_embed(pc, xo)
+    assert rel(out, ref) < 1e-2
+    (out * probe).sum().backward()
+    assert rel(xo.grad, xr.grad) < 1e-2
+    for k, p in pc.named_parameters():
+        assert rel(p.grad, ref_grads[k]) < 1.5e-2, k
