@@ -10,6 +10,9 @@
 // v1 data path: 64x64 tiles, 4 warps per CTA, bf16 mma.sync m16n8k16 with fp32 accumulators held in registers, online
 // softmax in registers with quad shuffles, K/V (or Q/dO) tiles double-buffered in XOR-swizzled shared memory via
 // cp.async.  Ragged S is handled by zero-filled loads + -inf key masking + predicated stores.
+#include <stdlib.h>
+#include <string.h>
+
 #include "../../include/tavk.h"
 #include "common.cuh"
 
@@ -453,6 +456,19 @@ static int check_common(const void* q, const void* k, const void* v, long long l
     return 0;
 }
 
+// attention_tc.cu: tcgen05/TMEM kernels (mask-free mode)
+int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream);
+
+// TAVK_ATTN_IMPL=legacy forces the mma.sync kernels everywhere (A/B testing); default: tcgen05 where it applies
+static bool use_tc_path() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TAVK_ATTN_IMPL");
+        v = (e != nullptr && strcmp(e, "legacy") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 }  // namespace tavk
 
 using namespace tavk;
@@ -464,6 +480,7 @@ extern "C" int tavk_attn_fwd(const tavk_attn_args* a, void* stream_) {
     if (rc) return rc;
     TAVK_CHECK(a->o != nullptr && a->ld_o % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, 1,
                "tavk_attn_fwd: bad output");
+    if (a->mode == TAVK_ATTN_NONE && a->S >= 128 && use_tc_path()) return attn_fwd_tc_launch(a, stream);
     AttnFwdDev d;
     d.q = reinterpret_cast<const __nv_bfloat16*>(a->q);
     d.k = reinterpret_cast<const __nv_bfloat16*>(a->k);
