@@ -458,6 +458,7 @@ static int check_common(const void* q, const void* k, const void* v, long long l
 
 // attention_tc.cu: tcgen05/TMEM kernels (mask-free mode)
 int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream);
+int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream);
 
 // TAVK_ATTN_IMPL=legacy forces the mma.sync kernels everywhere (A/B testing); default: tcgen05 where it applies
 static bool use_tc_path() {
@@ -533,6 +534,8 @@ extern "C" int tavk_attn_bwd(const tavk_attn_bwd_args* a, void* stream_) {
     attn_delta_kernel<<<(int)((pairs * 8 + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a->o), d.d_o, a->ld_o, a->delta, a->B, a->S, a->nh);
     TAVK_CUDA(cudaGetLastError());
+
+    if (a->mode == TAVK_ATTN_NONE && a->S >= 128 && use_tc_path()) return attn_bwd_tc_launch(a, stream);
 
     constexpr int kSmemDq = 6 * kTileBytes;
     constexpr int kSmemDkv = 6 * kTileBytes + 4 * kTile * (int)sizeof(float);

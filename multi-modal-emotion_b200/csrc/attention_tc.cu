@@ -257,6 +257,365 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
 }
 
+// =====================================================================================================
+// Backward (mask-free mode), two tcgen05 kernels that recompute P from the saved log-sum-exp:
+//   dK/dV kernel: CTA = 128 keys of one (b,h); loops over 64-query steps.
+//       S^T = K Q_i^T, dP^T = V dO_i^T               (UMMA 128x64x16 x4 each -> TMEM, double-buffered)
+//       P^T = ex2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)   (8 warps, thread = key row x 32 query columns)
+//       dV += P^T dO_i, dK += dS^T Q_i               (A = bf16 P^T / dS^T from smem, B = dO_i / Q_i MN-major)
+//   dQ kernel:    CTA = 128 queries; loops over 64-key steps.
+//       S = Q K_j^T, dP = dO V_j^T -> dS = ex2(S c - lse_row)(dP - delta_row) -> dQ += dS K_j
+// No atomics, deterministic.  Queries >= S are neutralised with lse = +inf (P = 0), keys >= S by zeroing P.
+// =====================================================================================================
+constexpr int kBwStep = 64;                              // inner-loop tile (queries for dK/dV, keys for dQ)
+constexpr int kBwStages = 4;
+constexpr int kBwSmall = kBwStep * kTcD * 2;             // 8 KB
+constexpr int kBwThreads = 10 * 32;                      // producer, MMA, 8 elementwise warps
+constexpr int kBwPBytes = 128 * kBwStep * 2;             // 16 KB: [128 rows][64 k] bf16, one SW128 atom column
+constexpr int kDkvSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 4 * kBwPBytes + 1024 + 256;
+constexpr int kDqSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 2 * kBwPBytes + 1024 + 256;
+
+struct AttnTcBwdDev {
+    const float *lse, *delta;
+    __nv_bfloat16 *dq, *dk, *dv;
+    long long ld_dqkv;
+    const float *dv_rowscale, *dv_rank1;
+    int B, S, nh;
+    float scale, scale_log2;
+};
+
+// 32 fp32 accumulator columns of this thread's row -> bf16 -> 64 contiguous bytes in global
+TAVK_DEVINL void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+}
+// 32 packed-pair registers (= 64 bf16... here 16 regs = 32 bf16) -> this row's 4 swizzled 16-byte chunks
+TAVK_DEVINL void st_row_chunks(uint32_t tile_base, int row, int half, const uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t addr = tile_base + row * 128 + ((((half << 2) + c) ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                     : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                       const AttnTcBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + kTcTile;
+    uint8_t* sQ = sV + kTcTile;                       // ring: [stage] Q_i
+    uint8_t* sDO = sQ + kBwStages * kBwSmall;         // ring: [stage] dO_i
+    uint8_t* sP = sDO + kBwStages * kBwSmall;         // [2] P^T
+    uint8_t* sDS = sP + 2 * kBwPBytes;                // [2] dS^T
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBwPBytes);
+    uint64_t* kv_full = bars;
+    uint64_t* qdo_full = bars + 1;
+    uint64_t* qdo_empty = qdo_full + kBwStages;
+    uint64_t* st_full = qdo_empty + kBwStages;   // 2
+    uint64_t* pds_full = st_full + 2;            // 2
+    uint64_t* pds_empty = pds_full + 2;          // 2
+    uint64_t* done = pds_empty + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < kBwStages; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&pds_full[i], 8); mbar_init(&pds_empty[i], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * kTcTile);
+            tma_load_3d(sK, &tmap_k, kv_full, h * kTcD, k0, b);
+            tma_load_3d(sV, &tmap_v, kv_full, h * kTcD, k0, b);
+            for (int i = 0; i < n_steps; ++i) {
+                const int st = i % kBwStages;
+                mbar_wait(&qdo_empty[st], ((i / kBwStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
+                tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
+                tma_load_3d(sDO + st * kBwSmall, &tmap_do, &qdo_full[st], h * kTcD, i * kBwStep, b);
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S^T, dP^T
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dV, dK (B MN-major)
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            mbar_wait(kv_full, 0);
+            tc_fence_after();
+            for (int i = 0; i <= n_steps; ++i) {
+                if (i < n_steps) {
+                    const int st = i % kBwStages;
+                    mbar_wait(&qdo_full[st], (i / kBwStages) & 1);
+                    tc_fence_after();
+                    const uint32_t q_addr = smem_u32(sQ + st * kBwSmall), do_addr = smem_u32(sDO + st * kBwSmall);
+                    const uint32_t t_st = tmem_base + (i & 1) * 128, t_dp = t_st + 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(t_st, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024),
+                                  idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(t_dp, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024),
+                                  idesc_kk, k > 0 ? 1u : 0u);
+                    umma_commit(&st_full[i & 1]);
+                }
+                if (i >= 1) {
+                    const int kstep = i - 1, st = kstep % kBwStages;
+                    mbar_wait(&pds_full[kstep & 1], (kstep >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t q_addr = smem_u32(sQ + st * kBwSmall), do_addr = smem_u32(sDO + st * kBwSmall);
+                    const uint32_t p_addr = smem_u32(sP + (kstep & 1) * kBwPBytes), ds_addr = smem_u32(sDS + (kstep & 1) * kBwPBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dv, umma_smem_desc(p_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 2048, 8192, 1024),
+                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dk, umma_smem_desc(ds_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 2048, 8192, 1024),
+                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&qdo_empty[st]);
+                    umma_commit(&pds_empty[kstep & 1]);
+                }
+            }
+            umma_commit(done);
+        }
+    } else {
+        const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
+        const int row = quarter * 32 + lane;                       // key row inside the tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const long long stat_off = ((long long)b * p.nh + h) * p.S;
+        for (int i = 0; i < n_steps; ++i) {
+            // per-column statistics of this thread's 32 queries (uniform addresses across the warp: broadcast loads)
+            float lse2[32], dlt[32];
+            const int qc0 = i * kBwStep + half * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const bool ok = qc0 + c < p.S;
+                lse2[c] = ok ? __ldg(p.lse + stat_off + qc0 + c) * kTcLog2e : INFINITY;   // +inf -> P = 0
+                dlt[c] = ok ? __ldg(p.delta + stat_off + qc0 + c) : 0.f;
+            }
+            mbar_wait(&st_full[i & 1], (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t s[32], dp[32];
+            const uint32_t t_st = tmem_base + lane_sel + (uint32_t)((i & 1) * 128 + half * 32);
+            tmem_ld_32x32(t_st, s);
+            tmem_ld_32x32(t_st + 64, dp);
+            tmem_ld_wait();
+            uint32_t pk[16], dsk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2[c]));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2[c + 1]));
+                pk[c >> 1] = pack_bf16x2(p0, p1);
+                dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt[c]), p1 * (__uint_as_float(dp[c + 1]) - dlt[c + 1]));
+            }
+            if (i >= 2) mbar_wait(&pds_empty[i & 1], ((i >> 1) - 1) & 1);
+            st_row_chunks(smem_u32(sP + (i & 1) * kBwPBytes), row, half, pk);
+            st_row_chunks(smem_u32(sDS + (i & 1) * kBwPBytes), row, half, dsk);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pds_full[i & 1]);
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int key = k0 + row;
+        uint32_t r[32];
+        float v[32];
+        // dK
+        tmem_ld_32x32(tmem_dk + lane_sel + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+        const long long out_off = ((long long)b * p.S + key) * p.ld_dqkv + h * kTcD + half * 32;
+        if (key < p.S) store_row32_bf16(p.dk + out_off, v);
+        // dV (+ rank-1 term of the post-softmax mask: dV[b,k,h,:] += m[b,k] * dc[b,h,:])
+        tmem_ld_32x32(tmem_dv + lane_sel + half * 32, r);
+        tmem_ld_wait();
+        float w = 0.f;
+        const float* dc = nullptr;
+        if (p.dv_rowscale != nullptr && key < p.S) {
+            w = p.dv_rowscale[(long long)b * p.S + key];
+            dc = p.dv_rank1 + ((long long)b * p.nh + h) * kTcD + half * 32;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) + (dc ? w * __ldg(dc + c) : 0.f);
+        if (key < p.S) store_row32_bf16(p.dv + out_off, v);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                      const AttnTcBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sDO = smem + kTcTile;
+    uint8_t* sK = sDO + kTcTile;                      // ring
+    uint8_t* sV = sK + kBwStages * kBwSmall;          // ring
+    uint8_t* sDS = sV + kBwStages * kBwSmall;         // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBwPBytes);
+    uint64_t* qdo_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + kBwStages;
+    uint64_t* s_full = kv_empty + kBwStages;     // 2
+    uint64_t* ds_full = s_full + 2;              // 2
+    uint64_t* ds_empty = ds_full + 2;            // 2
+    uint64_t* done = ds_empty + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+        mbar_init(qdo_full, 1);
+        for (int i = 0; i < kBwStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_dq = tmem_base + 256;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qdo_full, 2 * kTcTile);
+            tma_load_3d(sQ, &tmap_q, qdo_full, h * kTcD, q0, b);
+            tma_load_3d(sDO, &tmap_do, qdo_full, h * kTcD, q0, b);
+            for (int j = 0; j < n_steps; ++j) {
+                const int st = j % kBwStages;
+                mbar_wait(&kv_empty[st], ((j / kBwStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * kBwSmall);
+                tma_load_3d(sK + st * kBwSmall, &tmap_k, &kv_full[st], h * kTcD, j * kBwStep, b);
+                tma_load_3d(sV + st * kBwSmall, &tmap_v, &kv_full[st], h * kTcD, j * kBwStep, b);
+            }
+        }
+    } else if (warp_idx == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S, dP
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
+            const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
+            mbar_wait(qdo_full, 0);
+            tc_fence_after();
+            for (int j = 0; j <= n_steps; ++j) {
+                if (j < n_steps) {
+                    const int st = j % kBwStages;
+                    mbar_wait(&kv_full[st], (j / kBwStages) & 1);
+                    tc_fence_after();
+                    const uint32_t k_addr = smem_u32(sK + st * kBwSmall), v_addr = smem_u32(sV + st * kBwSmall);
+                    const uint32_t t_s = tmem_base + (j & 1) * 128, t_dp = t_s + 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(t_s, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
+                                  idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(t_dp, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024),
+                                  idesc_kk, k > 0 ? 1u : 0u);
+                    umma_commit(&s_full[j & 1]);
+                }
+                if (j >= 1) {
+                    const int kstep = j - 1, st = kstep % kBwStages;
+                    mbar_wait(&ds_full[kstep & 1], (kstep >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t k_addr = smem_u32(sK + st * kBwSmall);
+                    const uint32_t ds_addr = smem_u32(sDS + (kstep & 1) * kBwPBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dq, umma_smem_desc(ds_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 2048, 8192, 1024),
+                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&kv_empty[st]);
+                    umma_commit(&ds_empty[kstep & 1]);
+                }
+            }
+            umma_commit(done);
+        }
+    } else {
+        const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
+        const int row = quarter * 32 + lane;                       // query row inside the tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const int qrow = q0 + row;
+        const long long stat_off = ((long long)b * p.nh + h) * p.S;
+        const float lse2 = qrow < p.S ? p.lse[stat_off + qrow] * kTcLog2e : INFINITY;
+        const float dlt = qrow < p.S ? p.delta[stat_off + qrow] : 0.f;
+        for (int j = 0; j < n_steps; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t s[32], dp[32];
+            const uint32_t t_s = tmem_base + lane_sel + (uint32_t)((j & 1) * 128 + half * 32);
+            tmem_ld_32x32(t_s, s);
+            tmem_ld_32x32(t_s + 64, dp);
+            tmem_ld_wait();
+            const int valid = p.S - (j * kBwStep + half * 32);     // key columns of this thread's slab that exist
+            uint32_t dsk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2));
+                float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2));
+                if (c >= valid) p0 = 0.f;
+                if (c + 1 >= valid) p1 = 0.f;
+                dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt), p1 * (__uint_as_float(dp[c + 1]) - dlt));
+            }
+            if (j >= 2) mbar_wait(&ds_empty[j & 1], ((j >> 1) - 1) & 1);
+            st_row_chunks(smem_u32(sDS + (j & 1) * kBwPBytes), row, half, dsk);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ds_full[j & 1]);
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+        uint32_t r[32];
+        float v[32];
+        tmem_ld_32x32(tmem_dq + lane_sel + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+        if (qrow < p.S) store_row32_bf16(p.dq + ((long long)b * p.S + qrow) * p.ld_dqkv + h * kTcD + half * 32, v);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // ---------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -310,6 +669,42 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
     attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(tq, tk, tv, d);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// delta must already hold rowsum(dO * O) (attention.cu: attn_delta_kernel)
+int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
+    CUtensorMap tq64, tk64, tv64, tdo64, tq128, tk128, tv128, tdo128;
+    const int cols = a->nh * kTcD;
+    int rc = 0;
+    if ((rc = make_tmap_bsd(&tq64, a->q, a->B, a->S, cols, a->ld_qkv, kBwStep))) return rc;
+    if ((rc = make_tmap_bsd(&tk64, a->k, a->B, a->S, cols, a->ld_qkv, kBwStep))) return rc;
+    if ((rc = make_tmap_bsd(&tv64, a->v, a->B, a->S, cols, a->ld_qkv, kBwStep))) return rc;
+    if ((rc = make_tmap_bsd(&tdo64, a->d_o, a->B, a->S, cols, a->ld_o, kBwStep))) return rc;
+    if ((rc = make_tmap_bsd(&tq128, a->q, a->B, a->S, cols, a->ld_qkv, 128))) return rc;
+    if ((rc = make_tmap_bsd(&tk128, a->k, a->B, a->S, cols, a->ld_qkv, 128))) return rc;
+    if ((rc = make_tmap_bsd(&tv128, a->v, a->B, a->S, cols, a->ld_qkv, 128))) return rc;
+    if ((rc = make_tmap_bsd(&tdo128, a->d_o, a->B, a->S, cols, a->ld_o, 128))) return rc;
+    AttnTcBwdDev d;
+    d.lse = a->lse; d.delta = a->delta;
+    d.dq = reinterpret_cast<__nv_bfloat16*>(a->dq);
+    d.dk = reinterpret_cast<__nv_bfloat16*>(a->dk);
+    d.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
+    d.ld_dqkv = a->ld_dqkv;
+    d.dv_rowscale = a->dv_rowscale; d.dv_rank1 = a->dv_rank1;
+    d.B = a->B; d.S = a->S; d.nh = a->nh;
+    d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
+        attr_done = true;
+    }
+    dim3 grid((a->S + 127) / 128, a->nh, a->B);
+    attn_bwd_dkv_tc_kernel<<<grid, kBwThreads, kDkvSmem, stream>>>(tq64, tk128, tv128, tdo64, d);
+    TAVK_CUDA(cudaGetLastError());
+    attn_bwd_dq_tc_kernel<<<grid, kBwThreads, kDqSmem, stream>>>(tq128, tk64, tv64, tdo128, d);
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
