@@ -78,7 +78,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* pv_done = p_empty + 2;          // 1
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
 
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
     const int q0 = blockIdx.x * kTcQ, h = blockIdx.y, b = blockIdx.z;
     const int n_tiles = (p.S + kTcKV - 1) / kTcKV;
 
@@ -96,7 +96,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_o = tmem_base + 256;
 
     if (warp_idx == 0) {
@@ -113,42 +113,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = umma_idesc_bf16(kTcQ, kTcKV, false, false);
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(kTcQ, kTcD, false, true);
-            const uint32_t q_addr = smem_u32(sQ);
-            auto issue_qk = [&](int j) {
-                const int st = j % kTcStages;
-                mbar_wait(&kv_full[st], (j / kTcStages) & 1);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sK + st * kTcTile);
+        // whole warp runs the loop (warp-uniform control flow and operands), one elected lane issues
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(kTcQ, kTcKV, false, false);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(kTcQ, kTcD, false, true);
+        const uint64_t dq0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+        const uint64_t dk0 = umma_smem_desc(smem_u32(sK), 16, 1024);
+        const uint64_t dv0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
+        const uint64_t dp0 = umma_smem_desc(smem_u32(sP), 16, 1024);
+        auto issue_qk = [&](int j) {
+            const int st = j % kTcStages;
+            mbar_wait(&kv_full[st], (j / kTcStages) & 1);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t dk = dk0 + (uint64_t)(st * (kTcTile >> 4));
                 const uint32_t tmem_s = tmem_base + (j & 1) * kTcKV;
 #pragma unroll
-                for (int k = 0; k < kTcD / 16; ++k)
-                    umma_bf16(tmem_s, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                              idesc_qk, k > 0 ? 1u : 0u);
+                for (int k = 0; k < kTcD / 16; ++k) umma_bf16(tmem_s, dq0 + 2 * k, dk + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
                 umma_commit(&s_full[j & 1]);
-            };
-            mbar_wait(q_full, 0);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_qk(j + 1);
+            mbar_wait(&p_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_qk(j + 1);
-                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-                tc_fence_after();
+            if (leader) {
                 const int st = j % kTcStages;
-                const uint32_t p_addr = smem_u32(sP + (j & 1) * kTcPBytes);
-                const uint32_t v_addr = smem_u32(sV + st * kTcTile);
+                const uint64_t dp = dp0 + (uint64_t)((j & 1) * (kTcPBytes >> 4));
+                const uint64_t dv = dv0 + (uint64_t)(st * (kTcTile >> 4));
 #pragma unroll
-                for (int k = 0; k < kTcKV / 16; ++k) {
-                    const uint64_t da = umma_smem_desc(p_addr + (k >> 2) * (kTcQ * 128) + (k & 3) * 32, 16, 1024);
-                    const uint64_t db = umma_smem_desc(v_addr + k * 2048, 8192, 1024);
-                    umma_bf16(tmem_o, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < kTcKV / 16; ++k)
+                    umma_bf16(tmem_o, dp + (uint64_t)((k >> 2) * ((kTcQ * 128) >> 4) + (k & 3) * 2), dv + (uint64_t)(k * (2048 >> 4)),
+                              idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[st]);
                 umma_commit(&p_empty[j & 1]);
                 umma_commit(pv_done);
             }
+            __syncwarp();
         }
     } else {
         // ===================== softmax / epilogue: thread = one query row = one TMEM lane =====================
@@ -325,7 +330,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     uint64_t* done = pds_empty + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
 
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_steps = (p.S + kBwStep - 1) / kBwStep;
 
@@ -341,7 +346,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
 
     if (warp_idx == 0) {
@@ -358,49 +363,51 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S^T, dP^T
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dV, dK (B MN-major)
-            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            mbar_wait(kv_full, 0);
-            tc_fence_after();
-            for (int i = 0; i <= n_steps; ++i) {
-                if (i < n_steps) {
-                    const int st = i % kBwStages;
-                    mbar_wait(&qdo_full[st], (i / kBwStages) & 1);
-                    tc_fence_after();
-                    const uint32_t q_addr = smem_u32(sQ + st * kBwSmall), do_addr = smem_u32(sDO + st * kBwSmall);
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S^T, dP^T
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dV, dK (B MN-major)
+        const uint64_t dK = umma_smem_desc(smem_u32(sK), 16, 1024), dV = umma_smem_desc(smem_u32(sV), 16, 1024);
+        const uint64_t dQk0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dDOk0 = umma_smem_desc(smem_u32(sDO), 16, 1024);
+        const uint64_t dQm0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dDOm0 = umma_smem_desc(smem_u32(sDO), 8192, 1024);
+        const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 16, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        mbar_wait(kv_full, 0);
+        tc_fence_after();
+        for (int i = 0; i <= n_steps; ++i) {
+            if (i < n_steps) {
+                const int st = i % kBwStages;
+                mbar_wait(&qdo_full[st], (i / kBwStages) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
                     const uint32_t t_st = tmem_base + (i & 1) * 128, t_dp = t_st + 64;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(t_st, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024),
-                                  idesc_kk, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(t_dp, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024),
-                                  idesc_kk, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
                     umma_commit(&st_full[i & 1]);
                 }
-                if (i >= 1) {
-                    const int kstep = i - 1, st = kstep % kBwStages;
-                    mbar_wait(&pds_full[kstep & 1], (kstep >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t q_addr = smem_u32(sQ + st * kBwSmall), do_addr = smem_u32(sDO + st * kBwSmall);
-                    const uint32_t p_addr = smem_u32(sP + (kstep & 1) * kBwPBytes), ds_addr = smem_u32(sDS + (kstep & 1) * kBwPBytes);
+                __syncwarp();
+            }
+            if (i >= 1) {
+                const int kstep = i - 1, st = kstep % kBwStages;
+                mbar_wait(&pds_full[kstep & 1], (kstep >> 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4)), po = (uint64_t)((kstep & 1) * (kBwPBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dv, umma_smem_desc(p_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 2048, 8192, 1024),
-                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_dv, dP0 + po + 2 * k, dDOm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dk, umma_smem_desc(ds_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 2048, 8192, 1024),
-                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_dk, dDS0 + po + 2 * k, dQm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&qdo_empty[st]);
                     umma_commit(&pds_empty[kstep & 1]);
                 }
+                __syncwarp();
             }
-            umma_commit(done);
         }
+        if (leader) umma_commit(done);
+        __syncwarp();
     } else {
         const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;                       // key row inside the tile
@@ -493,7 +500,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint64_t* done = ds_empty + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
 
-    const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_steps = (p.S + kBwStep - 1) / kBwStep;
 
@@ -509,7 +516,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_dq = tmem_base + 256;
 
     if (warp_idx == 0) {
@@ -526,45 +533,47 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S, dP
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
-            const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
-            mbar_wait(qdo_full, 0);
-            tc_fence_after();
-            for (int j = 0; j <= n_steps; ++j) {
-                if (j < n_steps) {
-                    const int st = j % kBwStages;
-                    mbar_wait(&kv_full[st], (j / kBwStages) & 1);
-                    tc_fence_after();
-                    const uint32_t k_addr = smem_u32(sK + st * kBwSmall), v_addr = smem_u32(sV + st * kBwSmall);
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S, dP
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
+        const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dDO = umma_smem_desc(smem_u32(sDO), 16, 1024);
+        const uint64_t dKk0 = umma_smem_desc(smem_u32(sK), 16, 1024), dVk0 = umma_smem_desc(smem_u32(sV), 16, 1024);
+        const uint64_t dKm0 = umma_smem_desc(smem_u32(sK), 8192, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        mbar_wait(qdo_full, 0);
+        tc_fence_after();
+        for (int j = 0; j <= n_steps; ++j) {
+            if (j < n_steps) {
+                const int st = j % kBwStages;
+                mbar_wait(&kv_full[st], (j / kBwStages) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
                     const uint32_t t_s = tmem_base + (j & 1) * 128, t_dp = t_s + 64;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(t_s, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024),
-                                  idesc_kk, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_s, dQ + 2 * k, dKk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(t_dp, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024),
-                                  idesc_kk, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dDO + 2 * k, dVk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
                     umma_commit(&s_full[j & 1]);
                 }
-                if (j >= 1) {
-                    const int kstep = j - 1, st = kstep % kBwStages;
-                    mbar_wait(&ds_full[kstep & 1], (kstep >> 1) & 1);
-                    tc_fence_after();
-                    const uint32_t k_addr = smem_u32(sK + st * kBwSmall);
-                    const uint32_t ds_addr = smem_u32(sDS + (kstep & 1) * kBwPBytes);
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int kstep = j - 1, st = kstep % kBwStages;
+                mbar_wait(&ds_full[kstep & 1], (kstep >> 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4)), po = (uint64_t)((kstep & 1) * (kBwPBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dq, umma_smem_desc(ds_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 2048, 8192, 1024),
-                                  idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_dq, dDS0 + po + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&kv_empty[st]);
                     umma_commit(&ds_empty[kstep & 1]);
                 }
+                __syncwarp();
             }
-            umma_commit(done);
         }
+        if (leader) umma_commit(done);
+        __syncwarp();
     } else {
         const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;                       // query row inside the tile

@@ -71,7 +71,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
-    const int warp_idx = threadIdx.x >> 5;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
 
     if (warp_idx == 0 && lane == 0) {
@@ -91,7 +91,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
 
@@ -133,39 +133,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp_idx == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int split = tile % p.k_splits;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        // ===================== MMA issuer: the whole warp walks the (warp-uniform) loop, one elected lane issues ====
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
+        const uint64_t da0 = A_MN ? umma_smem_desc(smem_u32(smem_a), 8192, 1024) : umma_smem_desc(smem_u32(smem_a), 16, 1024);
+        const uint64_t db0 = B_MN ? umma_smem_desc(smem_u32(smem_b), 8192, 1024) : umma_smem_desc(smem_u32(smem_b), 16, 1024);
+        constexpr uint64_t kAStep = A_MN ? (2048 >> 4) : (32 >> 4);   // descriptor address units (16 B) per UMMA_K
+        constexpr uint64_t kBStep = B_MN ? (2048 >> 4) : (32 >> 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int split = tile % p.k_splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+                if (leader) {
+                    const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kABytes >> 4));
+                    const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                                 : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16(tmem_d, da + k * kAStep, db + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
+            if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps =====================
