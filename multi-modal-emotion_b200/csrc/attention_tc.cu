@@ -26,8 +26,8 @@ constexpr int kTcQ = 128, kTcKV = 128, kTcD = 64;
 constexpr int kTcStages = 3;
 constexpr int kTcTile = kTcKV * kTcD * 2;            // 16 KB  (K, V, Q tiles)
 constexpr int kTcPBytes = kTcQ * kTcKV * 2;          // 32 KB  (P tile, two 64-key SW128 atoms)
-constexpr int kTcSmem = kTcTile * (1 + 2 * kTcStages) + 2 * kTcPBytes + 1024 + 256;
-constexpr int kTcThreads = 6 * 32;
+constexpr int kTcSmem = kTcTile * (1 + 2 * kTcStages) + 2 * kTcPBytes + 6 * 128 * 4 + 1024 + 256;
+constexpr int kTcThreads = 10 * 32;   // producer, MMA issuer, 8 softmax warps (2 per TMEM lane quarter)
 constexpr uint32_t kTcTmemCols = 512;                // S[2] 256 + O 64 -> next power of two
 constexpr float kTcLog2e = 1.4426950408889634f, kTcLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
@@ -68,7 +68,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint8_t* sK = smem + kTcTile;
     uint8_t* sV = sK + kTcStages * kTcTile;
     uint8_t* sP = sV + kTcStages * kTcTile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTcPBytes);
+    float* s_part = reinterpret_cast<float*>(sP + 2 * kTcPBytes);   // [2 tiles parity][2 halves][128] row max, [2][128] row sum
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 6 * 128);
     uint64_t* q_full = bars;               // 1
     uint64_t* kv_full = bars + 1;          // kTcStages
     uint64_t* kv_empty = kv_full + kTcStages;
@@ -88,7 +89,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tma_prefetch_desc(&tmap_v);
         mbar_init(q_full, 1);
         for (int i = 0; i < kTcStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1); }
         mbar_init(pv_done, 1);
         mbar_fence_init();
     }
@@ -156,34 +157,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             __syncwarp();
         }
     } else {
-        // ===================== softmax / epilogue: thread = one query row = one TMEM lane =====================
-        const int quarter = warp_idx & 3;
+        // ===================== softmax / epilogue: two threads per query row (TMEM lane), 64 key columns each ========
+        const int quarter = warp_idx & 3, half = (warp_idx - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const uint32_t pair_bar = 1 + quarter;          // named barrier shared by the two warps of this lane quarter
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            uint32_t sr[128];
-            const uint32_t ts = tmem_base + lane_sel + (uint32_t)((j & 1) * kTcKV);
+            uint32_t sr[64];
+            const uint32_t ts = tmem_base + lane_sel + (uint32_t)((j & 1) * kTcKV + half * 64);
             tmem_ld_32x32(ts + 0, reinterpret_cast<uint32_t(&)[32]>(sr[0]));
             tmem_ld_32x32(ts + 32, reinterpret_cast<uint32_t(&)[32]>(sr[32]));
-            tmem_ld_32x32(ts + 64, reinterpret_cast<uint32_t(&)[32]>(sr[64]));
-            tmem_ld_32x32(ts + 96, reinterpret_cast<uint32_t(&)[32]>(sr[96]));
             tmem_ld_wait();
-            const int valid = min(kTcKV, p.S - j * kTcKV);   // keys of this tile that exist
+            const int valid = p.S - (j * kTcKV + half * 64);   // key columns of this thread's slab that exist
             float mx = -INFINITY;
-            if (valid == kTcKV) {
+            if (valid >= 64) {
 #pragma unroll
-                for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
             } else {
 #pragma unroll
-                for (int c = 0; c < 128; ++c) {
+                for (int c = 0; c < 64; ++c) {
                     if (c >= valid) sr[c] = 0xff800000u;  // -inf
                     mx = fmaxf(mx, __uint_as_float(sr[c]));
                 }
             }
-            mx *= p.scale_log2;
+            // combine the two half-row maxima (double-buffered by tile parity: one named barrier per tile suffices)
+            float* mp = s_part + (j & 1) * 256;
+            mp[half * 128 + row] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mp[row], mp[128 + row]) * p.scale_log2;
             float factor = 1.0f;
             const bool grow = mx > m_used + kRescaleThreshold;   // always true on the first tile (m_used = -inf)
             if (grow) {
@@ -194,7 +198,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             float sum = 0.f;
             const float neg_m = -m_used;
 #pragma unroll
-            for (int c = 0; c < 128; c += 2) {
+            for (int c = 0; c < 64; c += 2) {
                 const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
                 const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
                 sum += p0 + p1;
@@ -203,28 +207,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             l += sum;
             // P[j&1] must no longer be read by PV(j-2)
             if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
-            const uint32_t pbase = smem_u32(sP + (j & 1) * kTcPBytes) + row * 128;
+            const uint32_t pbase = smem_u32(sP + (j & 1) * kTcPBytes) + half * (kTcQ * 128) + row * 128;
 #pragma unroll
-            for (int ch = 0; ch < 16; ++ch) {
-                const uint32_t addr = pbase + (ch >> 3) * (kTcQ * 128) + (((ch & 7) ^ (row & 7)) << 4);
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
                              "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
                              : "memory");
             }
-            // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
+            // rare: the running max moved -> rescale this warp's 32 rows x 32 columns of O (needs PV(j-1) retired)
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
                 uint32_t orow[32];
+                const uint32_t to = tmem_o + lane_sel + half * 32;
+                tmem_ld_32x32(to, orow);
+                tmem_ld_wait();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t to = tmem_o + lane_sel + half * 32;
-                    tmem_ld_32x32(to, orow);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
-                    tmem_st_32x32(to, orow);
-                }
+                for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
+                tmem_st_32x32(to, orow);
                 tmem_st_wait();
             }
             fence_proxy_async_smem();   // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
@@ -232,26 +233,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[j & 1]);
         }
-        // ---- epilogue
+        // ---- epilogue: total row sum = sum of the two halves; each thread normalises and stores 32 of the 64 columns
+        float* lp = s_part + 512;
+        lp[half * 128 + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        l = lp[row] + lp[128 + row];
         mbar_wait(pv_done, (n_tiles - 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;
         const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint32_t packed[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t orow[32];
-            tmem_ld_32x32(tmem_o + lane_sel + half * 32, orow);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; c += 2)
-                packed[half * 16 + (c >> 1)] = pack_bf16x2(__uint_as_float(orow[c]) * inv, __uint_as_float(orow[c + 1]) * inv);
-        }
+        uint32_t orow[32];
+        tmem_ld_32x32(tmem_o + lane_sel + half * 32, orow);
+        tmem_ld_wait();
         if (qrow < p.S) {
-            uint4* dst = reinterpret_cast<uint4*>(p.o + ((long long)b * p.S + qrow) * p.ld_o + h * kTcD);
+            float v[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-            if (p.lse) p.lse[((long long)b * p.nh + h) * p.S + qrow] = l > 0.f ? (m_used + log2f(l)) * kTcLn2 : -INFINITY;
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(orow[c]) * inv;
+            __nv_bfloat16* dst = p.o + ((long long)b * p.S + qrow) * p.ld_o + h * kTcD + half * 32;
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            if (p.lse && half == 0) p.lse[((long long)b * p.nh + h) * p.S + qrow] = l > 0.f ? (m_used + log2f(l)) * kTcLn2 : -INFINITY;
         }
     }
     tc_fence_before();
@@ -277,7 +281,7 @@ constexpr int kBwStages = 4;
 constexpr int kBwSmall = kBwStep * kTcD * 2;             // 8 KB
 constexpr int kBwThreads = 10 * 32;                      // producer, MMA, 8 elementwise warps
 constexpr int kBwPBytes = 128 * kBwStep * 2;             // 16 KB: [128 rows][64 k] bf16, one SW128 atom column
-constexpr int kDkvSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 4 * kBwPBytes + 1024 + 256;
+constexpr int kDkvSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 4 * kBwPBytes + kBwStages * 128 * 4 + 1024 + 256;
 constexpr int kDqSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 2 * kBwPBytes + 1024 + 256;
 
 struct AttnTcBwdDev {
@@ -320,7 +324,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     uint8_t* sDO = sQ + kBwStages * kBwSmall;         // ring: [stage] dO_i
     uint8_t* sP = sDO + kBwStages * kBwSmall;         // [2] P^T
     uint8_t* sDS = sP + 2 * kBwPBytes;                // [2] dS^T
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBwPBytes);
+    float* s_stats = reinterpret_cast<float*>(sDS + 2 * kBwPBytes);   // ring: [stage][64 lse*log2e | 64 delta]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + kBwStages * 128);
     uint64_t* kv_full = bars;
     uint64_t* qdo_full = bars + 1;
     uint64_t* qdo_empty = qdo_full + kBwStages;
@@ -337,7 +342,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
         mbar_init(kv_full, 1);
-        for (int i = 0; i < kBwStages; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+        for (int i = 0; i < kBwStages; ++i) { mbar_init(&qdo_full[i], 2); mbar_init(&qdo_empty[i], 1); }  // TMA + stats
         for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&pds_full[i], 8); mbar_init(&pds_empty[i], 1); }
         mbar_init(done, 1);
         mbar_fence_init();
@@ -350,17 +355,30 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
 
     if (warp_idx == 0) {
+        // producer: lane 0 drives TMA; all lanes stage the per-query statistics of the step (lse*log2e, delta)
+        const long long stat_off = ((long long)b * p.nh + h) * p.S;
         if (lane == 0) {
             mbar_arrive_expect_tx(kv_full, 2 * kTcTile);
             tma_load_3d(sK, &tmap_k, kv_full, h * kTcD, k0, b);
             tma_load_3d(sV, &tmap_v, kv_full, h * kTcD, k0, b);
-            for (int i = 0; i < n_steps; ++i) {
-                const int st = i % kBwStages;
-                mbar_wait(&qdo_empty[st], ((i / kBwStages) & 1) ^ 1);
+        }
+        for (int i = 0; i < n_steps; ++i) {
+            const int st = i % kBwStages;
+            mbar_wait(&qdo_empty[st], ((i / kBwStages) & 1) ^ 1);
+            if (lane == 0) {
                 mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
                 tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
                 tma_load_3d(sDO + st * kBwSmall, &tmap_do, &qdo_full[st], h * kTcD, i * kBwStep, b);
             }
+#pragma unroll
+            for (int t = lane; t < kBwStep; t += 32) {
+                const int qi = i * kBwStep + t;
+                const bool ok = qi < p.S;
+                s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
+                s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qdo_full[st]);
         }
     } else if (warp_idx == 1) {
         const bool leader = elect_one();
@@ -412,16 +430,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;                       // key row inside the tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        const long long stat_off = ((long long)b * p.nh + h) * p.S;
         for (int i = 0; i < n_steps; ++i) {
-            // per-column statistics of this thread's 32 queries (uniform addresses across the warp: broadcast loads)
+            // per-column statistics of this thread's 32 queries, staged in smem by the producer (broadcast LDS.128)
+            const int stg = i % kBwStages;
+            mbar_wait(&qdo_full[stg], (i / kBwStages) & 1);
             float lse2[32], dlt[32];
-            const int qc0 = i * kBwStep + half * 32;
+            const float4* st4 = reinterpret_cast<const float4*>(s_stats + stg * 128 + half * 32);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const bool ok = qc0 + c < p.S;
-                lse2[c] = ok ? __ldg(p.lse + stat_off + qc0 + c) * kTcLog2e : INFINITY;   // +inf -> P = 0
-                dlt[c] = ok ? __ldg(p.delta + stat_off + qc0 + c) : 0.f;
+            for (int c = 0; c < 8; ++c) {
+                const float4 a = st4[c], d4 = st4[16 + c];
+                lse2[4 * c] = a.x; lse2[4 * c + 1] = a.y; lse2[4 * c + 2] = a.z; lse2[4 * c + 3] = a.w;
+                dlt[4 * c] = d4.x; dlt[4 * c + 1] = d4.y; dlt[4 * c + 2] = d4.z; dlt[4 * c + 3] = d4.w;
             }
             mbar_wait(&st_full[i & 1], (i >> 1) & 1);
             tc_fence_after();
