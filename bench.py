@@ -305,7 +305,7 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
     import collections
 
     sigs = collections.Counter(L.gemm_log)
-    total_flops, total_ms = 0.0, 0.0
+    total_flops, total_ms, table = 0.0, 0.0, []
     for sig, count in sigs.items():
         M, N, K, a_mn, b_mn, epi, out_bf16, has_bias, has_resid, has_rb, acc, ks = sig
         A = torch.randn((K, M) if a_mn else (M, K), device="cuda").bfloat16()
@@ -332,8 +332,15 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
             L.gemm(A, Bm, out, **kw)
         e1.record()
         torch.cuda.synchronize()
-        total_ms += count * e0.elapsed_time(e1) / reps
+        ms = e0.elapsed_time(e1) / reps
+        total_ms += count * ms
         total_flops += count * 2.0 * M * N * K
+        table.append((count * ms, count, ms, 2.0 * M * N * K / ms / 1e9, sig))
+    if os.environ.get("TAVK_GEMM_TABLE"):
+        with open(os.environ["TAVK_GEMM_TABLE"], "w") as f:
+            f.write("total_ms count ms_each TFLOP/s (M,N,K,a_mn,b_mn,epi,out_bf16,bias,resid,rowbias,acc,k_splits)\n")
+            for row in sorted(table, reverse=True):
+                f.write("%8.3f %4d %8.4f %7.1f %s\n" % row)
     achieved = total_flops / (total_ms * 1e-3) / 1e12 if total_ms > 0 else 0.0
     peak = peaks["bf16_tflops"]
     roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

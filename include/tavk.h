@@ -71,6 +71,9 @@ typedef struct tavk_gemm_args {
     const float* resid; int64_t ldr;                     /* f32 [M,N] residual or NULL                           */
     const float* rowbias; int32_t rows_per_group;        /* f32 [ceil(M/rows_per_group), N] or NULL              */
     const void* aux;  int64_t ldaux;                     /* bf16 [M,N] pre-activation, TAVK_EPI_GELU_BWD only    */
+    float* colsum;                                       /* f32 [N] or NULL: += column sums of the stored result
+                                                            (the bias gradient of the Linear that produced the
+                                                            GEMM's A operand), accumulated with red.global.add  */
     int32_t epilogue;                                    /* TAVK_EPI_*                                           */
     int32_t accumulate;                                  /* 1: out += result (f32 out, red.global.add)           */
     int32_t k_splits;                                    /* >=1; >1 requires accumulate                          */

@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("rowbias", C.c_void_p), ("rows_per_group", C.c_int32),
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("k_splits", C.c_int32), ("block_n", C.c_int32),
         ("alpha", C.c_float),
     ]
@@ -146,8 +147,8 @@ def require_device():
 
 # ------------------------------------------------------------------------------------------------ typed wrappers
 def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2=None, bias=None, resid=None,
-         rowbias=None, rows_per_group=0, aux=None, epilogue=EPI_LINEAR, accumulate=False, k_splits=1, block_n=0,
-         alpha=1.0):
+         rowbias=None, rows_per_group=0, aux=None, colsum=None, epilogue=EPI_LINEAR, accumulate=False, k_splits=1,
+         block_n=0, alpha=1.0):
     """out[M,N] = epi(alpha * A·B^T).  A/B bf16 2-D tensors (or views); K-major: [rows,K]; MN-major: [K,rows]."""
     a = GemmArgs()
     a.A, a.lda, a.a_mn_major = A.data_ptr(), (lda if lda is not None else A.stride(0)), int(a_mn)
@@ -160,6 +161,7 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.resid, a.ldr = _ptr(resid), (resid.stride(0) if resid is not None else 0)
     a.rowbias, a.rows_per_group = _ptr(rowbias), rows_per_group
     a.aux, a.ldaux = _ptr(aux), (aux.stride(0) if aux is not None else 0)
+    a.colsum = _ptr(colsum)
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
     if record_gemms:
         gemm_log.append((M, N, K, int(a_mn), int(b_mn), epilogue, int(out.dtype == torch.bfloat16), int(bias is not None),

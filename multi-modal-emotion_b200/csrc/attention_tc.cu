@@ -32,11 +32,6 @@ constexpr uint32_t kTcTmemCols = 512;                // S[2] 256 + O 64 -> next 
 constexpr float kTcLog2e = 1.4426950408889634f, kTcLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
 
-TAVK_DEVINL float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 TAVK_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 TAVK_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(

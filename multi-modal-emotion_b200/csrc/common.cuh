@@ -50,6 +50,84 @@ TAVK_DEVINL float gelu_erf_grad(float x) {
     const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+
+// ---------------------------------------------------------------- packed fp32x2 math (Blackwell FFMA2 / FMUL2 / FADD2)
+// The GEMM epilogues are issue-slot bound (K = 768: ~24 slots per 32 outputs before the tensor pipe waits), so the
+// polynomial work runs two outputs per instruction.
+struct f32x2 {
+    unsigned long long u;
+};
+TAVK_DEVINL f32x2 pk(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(lo), "f"(hi));
+    return r;
+}
+TAVK_DEVINL void unpk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.u)); }
+TAVK_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+    return r;
+}
+TAVK_DEVINL f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+    return r;
+}
+TAVK_DEVINL f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+    return r;
+}
+TAVK_DEVINL float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+TAVK_DEVINL float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// erf via Abramowitz & Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| <= 3e-7 for z >= 0.  The
+// coefficients below are pre-scaled by 2^(-k/2) so the polynomial takes |x| directly (z = |x|/sqrt 2).  Returns
+// r = (...)^-16 = 1 - erf(|x|/sqrt 2) for two inputs; measured |gelu - exact| < 1e-6, |gelu' - exact| < 1e-6 over
+// [-12, 12] in fp32 (three orders below the bf16 rounding of the stored result).
+TAVK_DEVINL f32x2 erfc_abs2(f32x2 ax) {
+    f32x2 p = fma2(pk(5.38297500e-06f, 5.38297500e-06f), ax, pk(4.88906356e-05f, 4.88906356e-05f));
+    p = fma2(p, ax, pk(3.80035750e-05f, 3.80035750e-05f));
+    p = fma2(p, ax, pk(3.27762632e-03f, 3.27762632e-03f));
+    p = fma2(p, ax, pk(2.11410062e-02f, 2.11410062e-02f));
+    p = fma2(p, ax, pk(4.98673470e-02f, 4.98673470e-02f));
+    p = fma2(p, ax, pk(1.0f, 1.0f));
+    p = mul2(p, p);
+    p = mul2(p, p);
+    p = mul2(p, p);
+    p = mul2(p, p);
+    float lo, hi;
+    unpk(p, lo, hi);
+    return pk(rcp_approx(lo), rcp_approx(hi));
+}
+// gelu(x) = 0.5 (x + |x| erf(|x|/sqrt 2)) = 0.5 (x + |x| - |x| r)
+TAVK_DEVINL void gelu_fast2(float x0, float x1, float& g0, float& g1) {
+    const f32x2 x = pk(x0, x1), ax = pk(fabsf(x0), fabsf(x1));
+    const f32x2 r = erfc_abs2(ax);
+    const f32x2 t = fma2(mul2(ax, r), pk(-1.0f, -1.0f), ax);
+    const f32x2 h = pk(0.5f, 0.5f);
+    unpk(fma2(x, h, mul2(t, h)), g0, g1);
+}
+// v *= gelu'(x) = Phi(x) + x phi(x), Phi(x) = 0.5 + copysign(0.5 - 0.5 r, x)
+TAVK_DEVINL void gelu_grad_mul2(float x0, float x1, float& v0, float& v1) {
+    const f32x2 x = pk(x0, x1), ax = pk(fabsf(x0), fabsf(x1));
+    const f32x2 r = erfc_abs2(ax);
+    float h0, h1;
+    unpk(fma2(r, pk(-0.5f, -0.5f), pk(0.5f, 0.5f)), h0, h1);
+    const f32x2 cdf = add2(pk(copysignf(h0, x0), copysignf(h1, x1)), pk(0.5f, 0.5f));
+    float e0, e1;
+    unpk(mul2(mul2(x, x), pk(-0.72134752f, -0.72134752f)), e0, e1);   // -x^2/2 * log2(e)
+    const f32x2 pdf = pk(ex2_approx(e0), ex2_approx(e1));
+    const f32x2 g = fma2(mul2(x, pk(0.3989422804f, 0.3989422804f)), pdf, cdf);
+    unpk(mul2(pk(v0, v1), g), v0, v1);
+}
 TAVK_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -71,6 +149,23 @@ TAVK_DEVINL bool elect_one() {
         "}\n"
         : "=r"(pred));
     return pred != 0;
+}
+
+TAVK_DEVINL void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+TAVK_DEVINL float4 ld_shared_v4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
+// Read-once global data that another pointer of the same kernel may legally alias in the caller's eyes (residual vs
+// output): the non-coherent path lets the compiler hoist these loads above earlier stores.
+TAVK_DEVINL float4 ld_global_nc_v4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 // ---------------------------------------------------------------- mbarrier

@@ -7,7 +7,8 @@
 // B200 design (one CTA per SM, persistent over output tiles, warp-specialised):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_128B boxes, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16)
-//   warps 2..9  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> bias / GELU / residual / row-bias -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b.x32 -> smem transpose patch -> coalesced bias / GELU / residual /
+//                 row-bias / column-sum -> global)
 //   smem ring of kStages {A tile 128x64, B tile BLOCK_Nx64}; TMEM double-buffered accumulator so the
 //   epilogue of tile i overlaps the MMA main loop of tile i+1.
 // K-major operand tile  : one TMA box {64 k, rows}; UMMA desc SBO = 1024 B, K advance = +32 B per UMMA_K.
@@ -31,7 +32,8 @@ struct GemmCfg {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (256 or 512 columns)
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // one 32x32 fp32 transpose patch per epilogue warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmDev {
@@ -49,10 +51,134 @@ struct GemmDev {
     int rows_per_group;
     const __nv_bfloat16* aux;
     long long ldaux;
+    float* colsum;
     int epilogue;
     int accumulate;
     float alpha;
 };
+
+struct EpiCtx {
+    uint32_t tmem_acc;      // TMEM address of this warp's lane quarter, column 0 of the tile's accumulator
+    uint32_t stg;           // this warp's 4 KB staging patch (shared-memory address)
+    int lane, half, row_base, col_base;
+    bool use_bias, use_rb, use_res;
+    uint64_t* tmem_empty;
+};
+
+// One epilogue warp's share of one output tile: 32 accumulator rows x every second 32-column chunk.
+// TMEM -> registers (lane = row) -> XOR-swizzled smem patch -> registers in the COALESCED layout (8 lanes x 4 columns
+// cover one row's chunk, 4 rows per instruction), where bias / row-bias / residual / GELU / GELU' / column sums are
+// applied and the result stored: each global access of the warp touches 4 full 128-byte (fp32) or 64-byte (bf16) row
+// segments instead of 32 rows x 16 B.  The chunk's global operands (residual, pre-activation) are requested BEFORE
+// the TMEM read so their latency hides behind it.
+template <int BLOCK_N, int MODE>
+TAVK_DEVINL void epilogue_tile(const GemmDev& p, const EpiCtx& cx) {
+    constexpr int kChunks = BLOCK_N / 32;
+    const int lane = cx.lane;
+    const int cc = lane & 7;                // 4-column group inside the chunk
+    const int rsub = lane >> 3;             // row inside each group of 4
+    const uint32_t st_addr = cx.stg + lane * 128;
+#pragma unroll 1
+    for (int c = cx.half; c < kChunks; c += 2) {
+        const int col = cx.col_base + c * 32 + cc * 4;
+        const bool col_ok = col < p.N;          // N % 8 == 0: a 4-column group is in or out as a whole
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cx.use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        float4 res[8];
+        uint2 ax[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = cx.row_base + i * 4 + rsub;
+            const bool ok = row < p.M && col_ok;
+            if (MODE == TAVK_EPI_GELU_BWD) {
+                ax[i] = make_uint2(0u, 0u);
+                if (ok) ax[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + (long long)row * p.ldaux + col));
+            }
+            if (MODE == TAVK_EPI_LINEAR) {
+                res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cx.use_res && ok) res[i] = ld_global_nc_v4(p.resid + (long long)row * p.ldr + col);
+                if (cx.use_rb && ok) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(
+                        p.rowbias + (long long)(row / p.rows_per_group) * p.N + col));
+                    res[i].x += q4.x; res[i].y += q4.y; res[i].z += q4.z; res[i].w += q4.w;
+                }
+            }
+        }
+        uint32_t r[32];
+        tmem_ld_32x32(cx.tmem_acc + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (c + 2 >= kChunks) {
+            // this warp has read its whole share of the accumulator: hand the TMEM buffer back to the MMA issuer
+            // before the global-memory part of the last chunk
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.tmem_empty);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            st_shared_v4(st_addr + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + rsub;
+            const int row = cx.row_base + rl;
+            float4 v = ld_shared_v4(cx.stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
+            if (row < p.M && col_ok) {
+                v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
+                v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
+                if (MODE == TAVK_EPI_GELU) {
+                    // out = pre-activation (bf16), out2 = GELU(pre) (bf16)
+                    float4 g;
+                    gelu_fast2(v.x, v.y, g.x, g.y);
+                    gelu_fast2(v.z, v.w, g.z, g.w);
+                    uint2 a, gg;
+                    a.x = pack_bf16x2(v.x, v.y);  a.y = pack_bf16x2(v.z, v.w);
+                    gg.x = pack_bf16x2(g.x, g.y); gg.y = pack_bf16x2(g.z, g.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = a;
+                    *reinterpret_cast<uint2*>(p.out2 + (long long)row * p.ldo2 + col) = gg;
+                    v = g;
+                } else {
+                    if (MODE == TAVK_EPI_GELU_BWD) {
+                        // out = acc * gelu'(aux)
+                        const float2 a0 = unpack_bf16x2(ax[i].x), a1 = unpack_bf16x2(ax[i].y);
+                        gelu_grad_mul2(a0.x, a0.y, v.x, v.y);
+                        gelu_grad_mul2(a1.x, a1.y, v.z, v.w);
+                    } else {
+                        v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+                    }
+                    if (p.out_bf16) {
+                        uint2 a;
+                        a.x = pack_bf16x2(v.x, v.y); a.y = pack_bf16x2(v.z, v.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = a;
+                    } else {
+                        float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+                        if (p.accumulate) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y),
+                                         "f"(v.z), "f"(v.w)
+                                         : "memory");
+                        } else {
+                            *reinterpret_cast<float4*>(o) = v;
+                        }
+                    }
+                }
+                cs0 += v.x; cs1 += v.y; cs2 += v.z; cs3 += v.w;
+            }
+        }
+        if (p.colsum != nullptr) {
+            // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+            if (lane < 8 && col_ok)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(cs0), "f"(cs1),
+                             "f"(cs2), "f"(cs3)
+                             : "memory");
+        }
+        __syncwarp();   // the staging patch is rewritten by the next chunk
+    }
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -64,7 +190,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
@@ -174,7 +301,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int ew = warp_idx - 2;            // 0..7
         const int quarter = warp_idx & 3;       // TMEM lane quarter this warp may access
         const int half = ew >> 2;               // which half of the column chunks
-        constexpr int kChunks = BLOCK_N / 32;
+        const uint32_t stg = smem_u32(smem_stage) + ew * 4096;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int split = tile % p.k_splits;
@@ -185,122 +312,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * kBlockM + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row_base = m_blk * kBlockM + quarter * 32;
             const bool lead_split = (split == 0);
-            const float* rb_row =
-                (p.rowbias != nullptr && row_ok) ? p.rowbias + (long long)(row / p.rows_per_group) * p.N : nullptr;
-#pragma unroll 1
-            for (int c = half; c < kChunks; c += 2) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
-                tmem_ld_32x32(taddr, r);
-                tmem_ld_wait();
-                const int col0 = n_blk * BLOCK_N + c * 32;
-                if (row_ok && col0 < p.N) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-                    const int ncols = min(32, p.N - col0);  // multiple of 8 (N % 8 == 0 enforced on host)
-                    if (p.bias != nullptr && lead_split) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (j < ncols) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
-                        }
-                    }
-                    if (p.epilogue == TAVK_EPI_GELU) {
-                        // out = pre-activation (bf16), out2 = GELU(pre) (bf16)
-                        __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-                        __nv_bfloat16* o2 = p.out2 + (long long)row * p.ldo2 + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (j < ncols) {
-                                uint4 a, g;
-                                a.x = pack_bf16x2(v[j], v[j + 1]);     a.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                                a.z = pack_bf16x2(v[j + 4], v[j + 5]); a.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                                g.x = pack_bf16x2(gelu_erf(v[j]), gelu_erf(v[j + 1]));
-                                g.y = pack_bf16x2(gelu_erf(v[j + 2]), gelu_erf(v[j + 3]));
-                                g.z = pack_bf16x2(gelu_erf(v[j + 4]), gelu_erf(v[j + 5]));
-                                g.w = pack_bf16x2(gelu_erf(v[j + 6]), gelu_erf(v[j + 7]));
-                                *reinterpret_cast<uint4*>(o1 + j) = a;
-                                *reinterpret_cast<uint4*>(o2 + j) = g;
-                            }
-                        }
-                    } else {
-                        if (p.epilogue == TAVK_EPI_GELU_BWD) {
-                            // out = acc * gelu'(aux)
-                            const __nv_bfloat16* ax = p.aux + (long long)row * p.ldaux + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                if (j < ncols) {
-                                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(ax + j));
-                                    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y),
-                                                 a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-                                    v[j] *= gelu_erf_grad(a0.x);     v[j + 1] *= gelu_erf_grad(a0.y);
-                                    v[j + 2] *= gelu_erf_grad(a1.x); v[j + 3] *= gelu_erf_grad(a1.y);
-                                    v[j + 4] *= gelu_erf_grad(a2.x); v[j + 5] *= gelu_erf_grad(a2.y);
-                                    v[j + 6] *= gelu_erf_grad(a3.x); v[j + 7] *= gelu_erf_grad(a3.y);
-                                }
-                            }
-                        }
-                        if (rb_row != nullptr && lead_split) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (j < ncols) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb_row + col0 + j));
-                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                                }
-                            }
-                        }
-                        if (p.resid != nullptr && lead_split) {
-                            const float* rr = p.resid + (long long)row * p.ldr + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (j < ncols) {
-                                    const float4 b4 = *reinterpret_cast<const float4*>(rr + j);
-                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                                }
-                            }
-                        }
-                        if (p.out_bf16) {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                if (j < ncols) {
-                                    uint4 a;
-                                    a.x = pack_bf16x2(v[j], v[j + 1]);     a.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                                    a.z = pack_bf16x2(v[j + 4], v[j + 5]); a.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                                    *reinterpret_cast<uint4*>(o + j) = a;
-                                }
-                            }
-                        } else {
-                            float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-                            if (p.accumulate) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    if (j < ncols) {
-                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
-                                                     "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                                                     : "memory");
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    if (j < ncols)
-                                        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            const bool use_bias = p.bias != nullptr && lead_split;
+            const bool use_rb = p.rowbias != nullptr && lead_split;
+            const bool use_res = p.resid != nullptr && lead_split;
+            EpiCtx cx;
+            cx.tmem_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            cx.stg = stg; cx.lane = lane; cx.half = half; cx.row_base = row_base; cx.col_base = n_blk * BLOCK_N;
+            cx.use_bias = use_bias; cx.use_rb = use_rb; cx.use_res = use_res;
+            cx.tmem_empty = &tmem_empty_bar[acc];
+            if (p.epilogue == TAVK_EPI_GELU) epilogue_tile<BLOCK_N, TAVK_EPI_GELU>(p, cx);
+            else if (p.epilogue == TAVK_EPI_GELU_BWD) epilogue_tile<BLOCK_N, TAVK_EPI_GELU_BWD>(p, cx);
+            else epilogue_tile<BLOCK_N, TAVK_EPI_LINEAR>(p, cx);
         }
     }
 
@@ -412,6 +436,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     d.bias = a->bias; d.resid = a->resid; d.ldr = a->ldr;
     d.rowbias = a->rowbias; d.rows_per_group = a->rows_per_group;
     d.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); d.ldaux = a->ldaux;
+    d.colsum = a->colsum;
     d.epilogue = a->epilogue; d.accumulate = a->accumulate; d.alpha = a->alpha;
 
     CUtensorMap ta, tb;
