@@ -30,7 +30,7 @@ enum { TAVK_F32 = 0, TAVK_BF16 = 1 };
 enum {
     TAVK_EPI_LINEAR = 0,   /* out = alpha*acc (+bias) (+rowbias) (+resid)                               */
     TAVK_EPI_GELU = 1,     /* out = bf16(pre), out2 = bf16(gelu_erf(pre)), pre = alpha*acc + bias      */
-    TAVK_EPI_GELU_BWD = 2  /* out = alpha*acc * gelu_erf'(aux) (+rowbias) (+resid)                     */
+    TAVK_EPI_GELU_BWD = 2  /* out = bf16((alpha*acc + bias) * gelu_erf'(aux)); bf16 output only             */
 };
 
 /* attention mask modes */

@@ -57,126 +57,206 @@ struct GemmDev {
     float alpha;
 };
 
-struct EpiCtx {
-    uint32_t tmem_acc;      // TMEM address of this warp's lane quarter, column 0 of the tile's accumulator
-    uint32_t stg;           // this warp's 4 KB staging patch (shared-memory address)
-    int lane, half, row_base, col_base;
-    bool use_bias, use_rb, use_res;
-    uint64_t* tmem_empty;
+// ---------------------------------------------------------------------------------------------- epilogue
+// One epilogue warp owns 32 accumulator rows (its TMEM lane quarter) x every second 32-column chunk of each tile the
+// CTA visits.  Per chunk: TMEM -> registers (lane = row) -> XOR-swizzled 4 KB smem patch -> registers in the COALESCED
+// layout (8 lanes x 4 columns cover one row's chunk, 4 rows per instruction), where bias / row-bias / residual /
+// GELU / GELU' / column sums are applied and the result stored: each global access of the warp touches 4 full
+// 128-byte (fp32) or 64-byte (bf16) row segments instead of 32 rows x 16 B.
+// The chunk's global operands (residual + row-bias, or the saved pre-activation) are software-pipelined one chunk
+// ahead (across tile boundaries too) in two register buffers, and the per-row work is branch-free (predicated loads
+// and stores only) so the 16 independent GELU polynomial chains of a chunk interleave.
+struct EpiItem {
+    int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns
+    bool col_ok, lead;      // column group inside N; first K-split (applies bias / row-bias / residual)
 };
 
-// One epilogue warp's share of one output tile: 32 accumulator rows x every second 32-column chunk.
-// TMEM -> registers (lane = row) -> XOR-swizzled smem patch -> registers in the COALESCED layout (8 lanes x 4 columns
-// cover one row's chunk, 4 rows per instruction), where bias / row-bias / residual / GELU / GELU' / column sums are
-// applied and the result stored: each global access of the warp touches 4 full 128-byte (fp32) or 64-byte (bf16) row
-// segments instead of 32 rows x 16 B.  The chunk's global operands (residual, pre-activation) are requested BEFORE
-// the TMEM read so their latency hides behind it.
-template <int BLOCK_N, int MODE>
-TAVK_DEVINL void epilogue_tile(const GemmDev& p, const EpiCtx& cx) {
-    constexpr int kChunks = BLOCK_N / 32;
-    const int lane = cx.lane;
-    const int cc = lane & 7;                // 4-column group inside the chunk
-    const int rsub = lane >> 3;             // row inside each group of 4
-    const uint32_t st_addr = cx.stg + lane * 128;
-#pragma unroll 1
-    for (int c = cx.half; c < kChunks; c += 2) {
-        const int col = cx.col_base + c * 32 + cc * 4;
-        const bool col_ok = col < p.N;          // N % 8 == 0: a 4-column group is in or out as a whole
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cx.use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        float4 res[8];
-        uint2 ax[8];
+enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_RED = 2 };   // plain fp32 store | bf16 store | fp32 red.global.add (split-K / +=)
+
+template <int MODE>
+struct EpiOperands {        // what one chunk needs from global memory besides the accumulator
+    float4 b4;
+    float4 res[MODE == TAVK_EPI_LINEAR ? 8 : 1];
+    uint2 aux[MODE == TAVK_EPI_GELU_BWD ? 8 : 1];
+};
+
+template <int MODE>
+TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, EpiOperands<MODE>& o) {
+    o.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr && w.lead && w.col_ok) o.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + w.col));
+    if (MODE == TAVK_EPI_LINEAR) {
+        const bool use_res = p.resid != nullptr && w.lead;
+        const bool use_rb = p.rowbias != nullptr && w.lead;
+        const float* rp = p.resid + (long long)(w.row_base + rsub) * p.ldr + w.col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = cx.row_base + i * 4 + rsub;
-            const bool ok = row < p.M && col_ok;
-            if (MODE == TAVK_EPI_GELU_BWD) {
-                ax[i] = make_uint2(0u, 0u);
-                if (ok) ax[i] = __ldg(reinterpret_cast<const uint2*>(p.aux + (long long)row * p.ldaux + col));
-            }
-            if (MODE == TAVK_EPI_LINEAR) {
-                res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cx.use_res && ok) res[i] = ld_global_nc_v4(p.resid + (long long)row * p.ldr + col);
-                if (cx.use_rb && ok) {
+            const int row = w.row_base + i * 4 + rsub;
+            const bool ok = row < p.M && w.col_ok;
+            o.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_res && ok) o.res[i] = ld_global_nc_v4(rp + (long long)i * 4 * p.ldr);
+        }
+        if (use_rb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = w.row_base + i * 4 + rsub;
+                if (row < p.M && w.col_ok) {
                     const float4 q4 = __ldg(reinterpret_cast<const float4*>(
-                        p.rowbias + (long long)(row / p.rows_per_group) * p.N + col));
-                    res[i].x += q4.x; res[i].y += q4.y; res[i].z += q4.z; res[i].w += q4.w;
+                        p.rowbias + (long long)(row / p.rows_per_group) * p.N + w.col));
+                    o.res[i].x += q4.x; o.res[i].y += q4.y; o.res[i].z += q4.z; o.res[i].w += q4.w;
                 }
             }
         }
-        uint32_t r[32];
-        tmem_ld_32x32(cx.tmem_acc + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        if (c + 2 >= kChunks) {
-            // this warp has read its whole share of the accumulator: hand the TMEM buffer back to the MMA issuer
-            // before the global-memory part of the last chunk
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(cx.tmem_empty);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            st_shared_v4(st_addr + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+    }
+    if (MODE == TAVK_EPI_GELU_BWD) {
+        const __nv_bfloat16* ap = p.aux + (long long)(w.row_base + rsub) * p.ldaux + w.col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + rsub;
-            const int row = cx.row_base + rl;
-            float4 v = ld_shared_v4(cx.stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
-            if (row < p.M && col_ok) {
-                v.x = fmaf(v.x, p.alpha, b4.x); v.y = fmaf(v.y, p.alpha, b4.y);
-                v.z = fmaf(v.z, p.alpha, b4.z); v.w = fmaf(v.w, p.alpha, b4.w);
-                if (MODE == TAVK_EPI_GELU) {
-                    // out = pre-activation (bf16), out2 = GELU(pre) (bf16)
-                    float4 g;
-                    gelu_fast2(v.x, v.y, g.x, g.y);
-                    gelu_fast2(v.z, v.w, g.z, g.w);
-                    uint2 a, gg;
-                    a.x = pack_bf16x2(v.x, v.y);  a.y = pack_bf16x2(v.z, v.w);
-                    gg.x = pack_bf16x2(g.x, g.y); gg.y = pack_bf16x2(g.z, g.w);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = a;
-                    *reinterpret_cast<uint2*>(p.out2 + (long long)row * p.ldo2 + col) = gg;
-                    v = g;
+            const int row = w.row_base + i * 4 + rsub;
+            o.aux[i] = make_uint2(0u, 0u);
+            if (row < p.M && w.col_ok) o.aux[i] = ld_global_nc_v2(ap + (long long)i * 4 * p.ldaux);
+        }
+    }
+}
+
+template <int MODE, int OUT>
+TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperands<MODE>& o, uint32_t taddr, uint32_t stg,
+                             int lane, uint64_t* release_bar) {
+    const int cc = lane & 7, rsub = lane >> 3;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+    if (release_bar != nullptr) {
+        // last chunk of the tile for this warp: hand the TMEM buffer back to the MMA issuer before the global stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release_bar);
+    }
+    const uint32_t st_addr = stg + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        st_shared_v4(st_addr + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    // this lane's first output element; rows advance by 4 per step (pointer increments instead of 64-bit multiplies)
+    constexpr int kEsz = (OUT == OUT_BF16) ? 2 : 4;
+    char* op = reinterpret_cast<char*>(p.out) + ((long long)(w.row_base + rsub) * p.ldo + w.col) * kEsz;
+    const long long ostep = 4 * p.ldo * kEsz;
+    char* op2 = nullptr;
+    long long ostep2 = 0;
+    if (MODE == TAVK_EPI_GELU) {
+        op2 = reinterpret_cast<char*>(p.out2) + ((long long)(w.row_base + rsub) * p.ldo2 + w.col) * 2;
+        ostep2 = 4 * p.ldo2 * 2;
+    }
+    const f32x2 alpha2 = pk(p.alpha, p.alpha), blo = pk(o.b4.x, o.b4.y), bhi = pk(o.b4.z, o.b4.w);
+    f32x2 cslo = pk(0.f, 0.f), cshi = pk(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + rsub;
+        const bool ok = (w.row_base + rl) < p.M && w.col_ok;
+        float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
+        unpk(fma2(pk(v.x, v.y), alpha2, blo), v.x, v.y);
+        unpk(fma2(pk(v.z, v.w), alpha2, bhi), v.z, v.w);
+        if (MODE == TAVK_EPI_GELU) {
+            // out = pre-activation (bf16), out2 = GELU(pre) (bf16)
+            float4 g;
+            gelu_fast2(v.x, v.y, g.x, g.y);
+            gelu_fast2(v.z, v.w, g.z, g.w);
+            uint2 a, gg;
+            a.x = pack_bf16x2(v.x, v.y);  a.y = pack_bf16x2(v.z, v.w);
+            gg.x = pack_bf16x2(g.x, g.y); gg.y = pack_bf16x2(g.z, g.w);
+            if (ok) {
+                *reinterpret_cast<uint2*>(op) = a;
+                *reinterpret_cast<uint2*>(op2) = gg;
+            }
+            op2 += ostep2;
+        } else {
+            if (MODE == TAVK_EPI_GELU_BWD) {
+                // out = acc * gelu'(aux)
+                const float2 a0 = unpack_bf16x2(o.aux[i].x), a1 = unpack_bf16x2(o.aux[i].y);
+                gelu_grad_mul2(a0.x, a0.y, v.x, v.y);
+                gelu_grad_mul2(a1.x, a1.y, v.z, v.w);
+            } else {
+                v.x += o.res[i].x; v.y += o.res[i].y; v.z += o.res[i].z; v.w += o.res[i].w;
+            }
+            if (ok) {
+                if (OUT == OUT_BF16) {
+                    uint2 a;
+                    a.x = pack_bf16x2(v.x, v.y); a.y = pack_bf16x2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(op) = a;
+                } else if (OUT == OUT_RED) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(v.x), "f"(v.y), "f"(v.z),
+                                 "f"(v.w)
+                                 : "memory");
                 } else {
-                    if (MODE == TAVK_EPI_GELU_BWD) {
-                        // out = acc * gelu'(aux)
-                        const float2 a0 = unpack_bf16x2(ax[i].x), a1 = unpack_bf16x2(ax[i].y);
-                        gelu_grad_mul2(a0.x, a0.y, v.x, v.y);
-                        gelu_grad_mul2(a1.x, a1.y, v.z, v.w);
-                    } else {
-                        v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
-                    }
-                    if (p.out_bf16) {
-                        uint2 a;
-                        a.x = pack_bf16x2(v.x, v.y); a.y = pack_bf16x2(v.z, v.w);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col) = a;
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-                        if (p.accumulate) {
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y),
-                                         "f"(v.z), "f"(v.w)
-                                         : "memory");
-                        } else {
-                            *reinterpret_cast<float4*>(o) = v;
-                        }
-                    }
+                    *reinterpret_cast<float4*>(op) = v;
                 }
-                cs0 += v.x; cs1 += v.y; cs2 += v.z; cs3 += v.w;
+            }
+            if (p.colsum != nullptr) {      // uniform; rows past M contribute nothing
+                cslo = add2(cslo, pk(ok ? v.x : 0.f, ok ? v.y : 0.f));
+                cshi = add2(cshi, pk(ok ? v.z : 0.f, ok ? v.w : 0.f));
             }
         }
-        if (p.colsum != nullptr) {
-            // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
-            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
-            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
-            if (lane < 8 && col_ok)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + col), "f"(cs0), "f"(cs1),
-                             "f"(cs2), "f"(cs3)
-                             : "memory");
+        op += ostep;
+    }
+    if (MODE != TAVK_EPI_GELU && p.colsum != nullptr) {
+        // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
+        float cs0, cs1, cs2, cs3;
+        unpk(cslo, cs0, cs1);
+        unpk(cshi, cs2, cs3);
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+        if (lane < 8 && w.col_ok)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + w.col), "f"(cs0), "f"(cs1),
+                         "f"(cs2), "f"(cs3)
+                         : "memory");
+    }
+    __syncwarp();   // the staging patch is rewritten by the next chunk
+}
+
+template <int BLOCK_N, int MODE, int OUT>
+TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t stg, int lane, int quarter, int half,
+                               int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+    constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (2 or 4: always even)
+    const int cc = lane & 7, rsub = lane >> 3;
+    auto item = [&](int tile, int ci) {
+        EpiItem w;
+        const int mn = tile / p.k_splits;
+        w.lead = (tile % p.k_splits) == 0;
+        w.row_base = (mn / p.num_n_blocks) * kBlockM + quarter * 32;
+        w.col = (mn % p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32 + cc * 4;
+        w.col_ok = w.col < p.N;             // N % 8 == 0: a 4-column group is in or out as a whole
+        return w;
+    };
+    EpiOperands<MODE> opA, opB;
+    EpiItem wA, wB;
+    int tile = blockIdx.x;
+    if (tile < num_tiles) {
+        wA = item(tile, 0);
+        epi_issue_loads<MODE>(p, wA, rsub, opA);
+    }
+    int it = 0;
+    for (; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 32);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ci = 0; ci < kPer; ci += 2) {
+            wB = item(tile, ci + 1);
+            epi_issue_loads<MODE>(p, wB, rsub, opB);
+            epi_process<MODE, OUT>(p, wA, opA, tacc + (uint32_t)(ci * 64), stg, lane, nullptr);
+            // next item for buffer A: two chunks on in this tile, or the first chunk of the CTA's next tile
+            const bool last = (ci + 2 >= kPer);
+            const int ntile = last ? tile + (int)gridDim.x : tile;
+            if (ntile < num_tiles) {
+                wA = item(ntile, last ? 0 : ci + 2);
+                epi_issue_loads<MODE>(p, wA, rsub, opA);
+            }
+            epi_process<MODE, OUT>(p, wB, opB, tacc + (uint32_t)((ci + 1) * 64), stg, lane,
+                                   last ? &tmem_empty_bar[acc] : nullptr);
         }
-        __syncwarp();   // the staging patch is rewritten by the next chunk
     }
 }
 
@@ -302,30 +382,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int quarter = warp_idx & 3;       // TMEM lane quarter this warp may access
         const int half = ew >> 2;               // which half of the column chunks
         const uint32_t stg = smem_u32(smem_stage) + ew * 4096;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int split = tile % p.k_splits;
-            const int mn = tile / p.k_splits;
-            const int n_blk = mn % p.num_n_blocks;
-            const int m_blk = mn / p.num_n_blocks;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
-            const int row_base = m_blk * kBlockM + quarter * 32;
-            const bool lead_split = (split == 0);
-            const bool use_bias = p.bias != nullptr && lead_split;
-            const bool use_rb = p.rowbias != nullptr && lead_split;
-            const bool use_res = p.resid != nullptr && lead_split;
-            EpiCtx cx;
-            cx.tmem_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            cx.stg = stg; cx.lane = lane; cx.half = half; cx.row_base = row_base; cx.col_base = n_blk * BLOCK_N;
-            cx.use_bias = use_bias; cx.use_rb = use_rb; cx.use_res = use_res;
-            cx.tmem_empty = &tmem_empty_bar[acc];
-            if (p.epilogue == TAVK_EPI_GELU) epilogue_tile<BLOCK_N, TAVK_EPI_GELU>(p, cx);
-            else if (p.epilogue == TAVK_EPI_GELU_BWD) epilogue_tile<BLOCK_N, TAVK_EPI_GELU_BWD>(p, cx);
-            else epilogue_tile<BLOCK_N, TAVK_EPI_LINEAR>(p, cx);
-        }
+#define TAVK_EPI(MODE, OUT) \
+    epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
+        if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI(TAVK_EPI_GELU, OUT_BF16);
+        else if (p.epilogue == TAVK_EPI_GELU_BWD) TAVK_EPI(TAVK_EPI_GELU_BWD, OUT_BF16);
+        else if (p.out_bf16) TAVK_EPI(TAVK_EPI_LINEAR, OUT_BF16);
+        else if (p.accumulate) TAVK_EPI(TAVK_EPI_LINEAR, OUT_RED);
+        else TAVK_EPI(TAVK_EPI_LINEAR, OUT_F32);
+#undef TAVK_EPI
     }
 
     tc_fence_before();
@@ -405,8 +469,8 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     TAVK_CHECK(k_splits == 1 || a->accumulate, 1, "tavk_gemm_bf16: split-K requires accumulate=1 (atomic adds)");
     TAVK_CHECK(a->epilogue != TAVK_EPI_GELU || (a->out_dtype == TAVK_BF16 && a->out2 != nullptr && k_splits == 1), 1,
                "tavk_gemm_bf16: GELU epilogue needs bf16 out + out2 and no split-K");
-    TAVK_CHECK(a->epilogue != TAVK_EPI_GELU_BWD || (a->aux != nullptr && k_splits == 1), 1,
-               "tavk_gemm_bf16: GELU_BWD epilogue needs aux and no split-K");
+    TAVK_CHECK(a->epilogue != TAVK_EPI_GELU_BWD || (a->aux != nullptr && k_splits == 1 && a->out_dtype == TAVK_BF16), 1,
+               "tavk_gemm_bf16: GELU_BWD epilogue needs aux, a bf16 output and no split-K");
     TAVK_CHECK(a->rowbias == nullptr || a->rows_per_group > 0, 1, "tavk_gemm_bf16: rowbias needs rows_per_group");
     const int vec = (a->out_dtype == TAVK_BF16) ? 8 : 4;
     TAVK_CHECK(a->ldo % vec == 0, 1, "tavk_gemm_bf16: ldo must be a multiple of %d", vec);

@@ -203,10 +203,9 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf):
         L.colsum(dy, g["b2"], M=M, N=H)
         g["w2"] = _wgrad(dy_bf, sv.act, H, I, M)
         dpre = _bf16((M, I), dev)
-        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD)
+        g["b1"] = zeros(I)   # column sums of dpre, accumulated by the GEMM epilogue
+        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=g["b1"])
         # FFN up
-        g["b1"] = _f32((I,), dev)
-        L.colsum(dpre, g["b1"], M=M, N=I)
         g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
         dh2 = _f32((M, H), dev)
         L.gemm(dpre, sh.w1, dh2, M=M, N=H, K=I, b_mn=True)
@@ -243,9 +242,8 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf):
         L.colsum(df, g["b2"], M=M, N=H)
         g["w2"] = _wgrad(df_bf, sv.act, H, I, M)
         dpre = _bf16((M, I), dev)
-        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD)
-        g["b1"] = _f32((I,), dev)
-        L.colsum(dpre, g["b1"], M=M, N=I)
+        g["b1"] = zeros(I)   # column sums of dpre, accumulated by the GEMM epilogue
+        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=g["b1"])
         g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
         dyl = _f32((M, H), dev)
         L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)

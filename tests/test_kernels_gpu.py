@@ -77,6 +77,14 @@ def test_gemm_epilogues(L):
     outg = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     L.gemm(A, W, outg, M=M, N=N, K=K, aux=pre, epilogue=L.EPI_GELU_BWD)
     assert rel_l2(outg, acc * x.grad) < 4e-3
+    # fused column sums of the stored result (the bias gradient of the producing Linear), accumulated into colsum
+    cs = torch.full((N,), 2.0, device="cuda")
+    L.gemm(A, W, outg, M=M, N=N, K=K, aux=pre, epilogue=L.EPI_GELU_BWD, colsum=cs)
+    assert rel_l2(cs, 2.0 + (acc * x.grad).sum(dim=0)) < 2e-3
+    cs = torch.zeros((N,), device="cuda")
+    out32 = torch.empty(M, N, device="cuda")
+    L.gemm(A, W, out32, M=M, N=N, K=K, bias=bias, colsum=cs)
+    assert rel_l2(cs, (acc + bias).sum(dim=0)) < 2e-3
     # accumulate + split-K (wgrad form)
     base = torch.randn(N, K, generator=g).cuda()
     out = base.clone()
