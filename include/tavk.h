@@ -169,6 +169,24 @@ int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float* dx, int64
 int tavk_permute_bshd_bhds(const void* in, void* out, int B, int S, int nh, int d, int inverse, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Wav2Vec2 convolutional feature encoder, first layer, channels-last (HF Wav2Vec2GroupNormConvLayer: Conv1d(1, C, k,
+ * stride s, bias optional) -> GroupNorm(C groups, eps) -> GELU; reached from the reference at models/tav.py:352
+ * (wav2vec2.feature_extractor) and :476 (wav2vec2(...))).  Activations are bf16 [B, R, C] with R >= T padded rows
+ * per sample (rows t >= T are zero); the layers after it run on tavk_gemm_bf16 with lda = stride*C (overlapping TMA
+ * rows), see multi-modal-emotion_b200/frontends.py.
+ *   conv0_fwd           : u[b,t,c] = sum_j wav[b, s*t+j] w[c,j] (+bias[c])          wav f32 [B,L], w f32 [C,k]
+ *   groupnorm_gelu_fwd  : per (b,c) mean/rstd over t < T (two-pass, f32); z = gamma*xhat+beta, a = gelu_erf(z)
+ *   groupnorm_conv0_bwd : from dz (gradient w.r.t. z, bf16): dgamma, dbeta, dw[C,k] (and dbias) are ACCUMULATED
+ *                         (atomics; zero them first); the waveform needs no gradient. */
+int tavk_conv0_fwd(const float* wav, const float* w, const float* bias, void* u_bf16, int B, int L, int R, int T, int C,
+                   int k, int s, void* stream);
+int tavk_groupnorm_gelu_fwd(const void* u_bf16, const float* gamma, const float* beta, void* z_bf16, void* a_bf16,
+                            float* mean, float* rstd, int B, int R, int T, int C, float eps, void* stream);
+int tavk_groupnorm_conv0_bwd(const void* dz_bf16, const void* u_bf16, const float* mean, const float* rstd,
+                             const float* gamma, const float* wav, float* dgamma, float* dbeta, float* dw, float* dbias,
+                             int B, int L, int R, int T, int C, int k, int s, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Weighted softmax cross-entropy (utils/global_functions.py:63-64,76,83 — nn.CrossEntropyLoss(weight=w), mean).
  * logits f32 [B,C], target int64 [B], class_weight f32 [C] or NULL (all ones).
  * Emits loss_num = sum_i w[y_i]*l_i and loss_den = sum_i w[y_i] separately (data-parallel ranks all-reduce the

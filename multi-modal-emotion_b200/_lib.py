@@ -85,6 +85,9 @@ SIGNATURES = {
     "tavk_dropout": [_P, _P, _P, _L, _F, _U64, _U64, _P, _P],
     "tavk_dropout_bwd": [_P, _P, _P, _L, _F, _P],
     "tavk_permute_bshd_bhds": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "tavk_conv0_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tavk_groupnorm_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tavk_groupnorm_conv0_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "tavk_softmax_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_softmax_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_grad_sqnorm": [_P, _L, _P, _P],

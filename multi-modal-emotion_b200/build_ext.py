@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libtavk.so")
 OBJ = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "pointwise.cu", "loss_optim.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "pointwise.cu", "loss_optim.cu",
+           "conv_frontend.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
     "-cudart", "shared", "--expt-relaxed-constexpr",

@@ -17,13 +17,132 @@ import torch.nn.functional as F
 from . import _lib as L
 from .engine import _wgrad
 
-# The 7-layer Conv1d feature extractor still runs in cuDNN; under bf16 autocast it uses the
-# bf16 tensor-core kernels (fp32 accumulate; GroupNorm / LayerNorm stay fp32) instead of TF32 + layout conversions.
+# Layer-norm feature encoders (wav2vec2-large family: Conv1d+bias -> LayerNorm -> GELU per layer) still run in cuDNN
+# under bf16 autocast; the group-norm family (wav2vec2-base, the benchmark workload) runs on the kernel library.
 FE_AUTOCAST = True
 
 
+def _fe_rows(L, kernels, strides):
+    """Valid frames T_l per layer and padded rows-per-sample R_l with R_{l-1} = stride_l * R_l (and s_0 * R_0 >= L):
+    with that padding the (b, t) rows of every layer form ONE matrix whose row pitch is stride*C."""
+    T, t = [], L
+    for k, st in zip(kernels, strides):
+        t = (t - k) // st + 1
+        T.append(t)
+    n = len(T)
+    suffix = [1] * n                      # product of strides of the layers above l
+    for l in range(n - 2, -1, -1):
+        suffix[l] = suffix[l + 1] * strides[l + 1]
+    r_last = max(-(-T[l] // suffix[l]) for l in range(n))
+    r_last = max(r_last, -(-L // (suffix[0] * strides[0])))
+    return T, [r_last * suffix[l] for l in range(n)]
+
+
+class _ConvFeatureEncoderFn(torch.autograd.Function):
+    """HF Wav2Vec2FeatureEncoder (feat_extract_norm="group", no conv bias) in channels-last layout: [B, L] f32 ->
+    [B, T, C] f32.  Layer 0 (C_in = 1) + GroupNorm + GELU are streaming kernels (csrc/conv_frontend.cu); every later
+    Conv1d(C, C, k, stride s) + GELU is one tcgen05 GEMM over the whole batch: A = previous activations with row pitch
+    s*C and row length k*C (overlapping TMA rows), B = the weight reordered to [C_out, (tap, c_in)], GELU epilogue.
+    Backward per layer: wgrad GEMM (both operands MN-major, split-K) and a dgrad GEMM that writes s input rows per
+    output row at once — A = [dpre(t-D+1) .. dpre(t)] (row pitch C, row length D*C, D = ceil(k/s)), B = the taps
+    regrouped by (input phase r, delay d) — with the previous layer's GELU' fused in its epilogue."""
+
+    @staticmethod
+    def forward(ctx, wav, gn_w, gn_b, eps, kernels, strides, *weights):
+        L.require_device()
+        B, Ls = wav.shape
+        C = weights[0].shape[0]
+        n = len(weights)
+        dev = wav.device
+        T, R = _fe_rows(Ls, kernels, strides)
+        wav = wav.contiguous().float()
+        Lp = Ls                            # reads past the clip (padding rows only) are predicated to zero
+        pad = 8                            # zeroed tail rows: the last padded rows of the last sample read past B*R
+        u0 = torch.empty((B * R[0], C), dtype=torch.bfloat16, device=dev)
+        L.call("tavk_conv0_fwd", wav.data_ptr(), weights[0].data_ptr(), None, u0.data_ptr(), B, Lp, R[0], T[0], C,
+               kernels[0], strides[0])
+        acts = [torch.zeros((B * R[l] + pad, C), dtype=torch.bfloat16, device=dev) for l in range(n)]
+        pres = [torch.empty((B * R[l], C), dtype=torch.bfloat16, device=dev) for l in range(n)]
+        mean = torch.empty((B, C), dtype=torch.float32, device=dev)
+        rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        L.call("tavk_groupnorm_gelu_fwd", u0.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), pres[0].data_ptr(),
+               acts[0].data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, R[0], T[0], C, float(eps))
+        for l in range(1, n):
+            k, st = kernels[l], strides[l]
+            wk = L.cast_bf16(weights[l].detach().permute(0, 2, 1).contiguous().view(C, k * C))
+            L.gemm(acts[l - 1], wk, pres[l], M=B * R[l], N=C, K=k * C, lda=st * C, out2=acts[l][:B * R[l]],
+                   epilogue=L.EPI_GELU)
+        ctx.save_for_backward(wav, u0, mean, rstd, gn_w, *weights, *acts[:-1], *pres)
+        ctx.meta = (B, Lp, C, n, T, R, tuple(kernels), tuple(strides))
+        return acts[-1][:B * R[-1]].view(B, R[-1], C)[:, :T[-1]].float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Lp, C, n, T, R, kernels, strides = ctx.meta
+        sv = ctx.saved_tensors
+        wav, u0, mean, rstd, gn_w = sv[:5]
+        weights, acts, pres = sv[5:5 + n], sv[5 + n:5 + 2 * n - 1], sv[5 + 2 * n - 1:]
+        dev = dy.device
+        # gradient w.r.t. the last pre-activation, in the padded row layout (padding rows stay exactly zero)
+        pre_top = pres[-1].view(B, R[-1], C)[:, :T[-1]].float()
+        dtop = torch.ops.aten.gelu_backward(dy.contiguous().float(), pre_top)
+        D = [-(-kernels[l] // strides[l]) for l in range(n)]
+        lead = D[-1] - 1
+        dpre = torch.zeros((lead + B * R[-1], C), dtype=torch.bfloat16, device=dev)
+        dpre[lead:].view(B, R[-1], C)[:, :T[-1]].copy_(dtop)
+        grads = [None] * n
+        for l in range(n - 1, 0, -1):
+            k, st, d = kernels[l], strides[l], D[l]
+            M = B * R[l]
+            cur = dpre[d - 1:]                           # [M, C] rows of this layer's dpre
+            # wgrad: dWk[n, (tap, c)] = sum_m dpre[m, n] * a_{l-1}[m*st*C + (tap, c)]
+            dwk = torch.zeros((C, k * C), dtype=torch.float32, device=dev)
+            tiles = ((C + 127) // 128) * ((k * C + 255) // 256)
+            ks = max(1, min(148 // tiles, (M + 511) // 512))
+            L.gemm(cur, acts[l - 1], dwk, M=C, N=k * C, K=M, lda=C, ldb=st * C, a_mn=True, b_mn=True, accumulate=True,
+                   k_splits=ks)
+            grads[l] = dwk.view(C, k, C).permute(0, 2, 1)
+            # dgrad (+ GELU' of layer l-1): out rows = s input rows each
+            w = weights[l].detach()
+            b2 = torch.zeros((st, C, d, C), dtype=torch.bfloat16, device=dev)
+            for r in range(st):
+                for dd in range(d):
+                    tap = r + st * dd
+                    if tap < k:
+                        b2[r, :, d - 1 - dd, :].copy_(w[:, :, tap].t())
+            lead_prev = D[l - 1] - 1 if l - 1 >= 1 else 0
+            nxt = torch.empty((lead_prev + B * R[l - 1], C), dtype=torch.bfloat16, device=dev)
+            if lead_prev:
+                nxt[:lead_prev].zero_()
+            L.gemm(dpre, b2.view(st * C, d * C), nxt[lead_prev:].view(M, st * C), M=M, N=st * C, K=d * C, lda=C,
+                   aux=pres[l - 1].view(M, st * C), epilogue=L.EPI_GELU_BWD)
+            dpre = nxt
+        # layer 0: GroupNorm + conv over the waveform (dpre now holds dz0)
+        dgw, dgb = torch.zeros_like(gn_w), torch.zeros_like(gn_w)
+        dw0 = torch.zeros_like(weights[0])
+        L.call("tavk_groupnorm_conv0_bwd", dpre.data_ptr(), u0.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               gn_w.data_ptr(), wav.data_ptr(), dgw.data_ptr(), dgb.data_ptr(), dw0.data_ptr(), None, B, Lp, R[0], T[0],
+               C, kernels[0], strides[0])
+        grads[0] = dw0
+        return (None, dgw, dgb, None, None, None, *grads)
+
+
+def feature_extractor_cl(w2v, wav):
+    """HF Wav2Vec2FeatureEncoder.forward in channels-last form: [B, L] -> [B, frames, C] (fp32)."""
+    fe = w2v.feature_extractor
+    c = w2v.config
+    layers = fe.conv_layers
+    if (c.feat_extract_norm == "group" and not c.conv_bias and c.feat_extract_activation == "gelu" and wav.is_cuda
+            and max(c.conv_kernel) <= 16 and layers[0].conv.weight.shape[0] % 16 == 0
+            and len(set(l.conv.weight.shape[0] for l in layers)) == 1):
+        gn = layers[0].layer_norm
+        return _ConvFeatureEncoderFn.apply(wav, gn.weight, gn.bias, gn.eps, tuple(c.conv_kernel), tuple(c.conv_stride),
+                                           *[l.conv.weight for l in layers])
+    return feature_extractor(w2v, wav).transpose(1, 2)
+
+
 def feature_extractor(w2v, wav):
-    """HF Wav2Vec2FeatureEncoder.forward: [B, L] -> [B, 512, frames] (fp32 out)."""
+    """HF Wav2Vec2FeatureEncoder.forward: [B, L] -> [B, C, frames] (fp32 out) through cuDNN (layer-norm family)."""
     if FE_AUTOCAST and wav.is_cuda:
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return w2v.feature_extractor(wav).float()

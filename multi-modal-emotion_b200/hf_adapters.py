@@ -98,7 +98,7 @@ def wav2vec2_layer_slots(lyr):
 
 def wav2vec2_front(model, wav):
     """feature_extractor (7 x Conv1d) -> transpose -> feature_projection (LN + Linear): [B,L] -> [B,Ta,H]."""
-    feats = frontends.feature_extractor(model, wav).transpose(1, 2)
+    feats = frontends.feature_extractor_cl(model, wav)      # channels-last [B, frames, C]
     hidden, _ = model.feature_projection(feats)
     return hidden
 

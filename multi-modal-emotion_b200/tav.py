@@ -133,10 +133,10 @@ class PreFormer(nn.Module):
         if input_ids is not None:
             embedded_bert = self.bert.embeddings(input_ids=input_ids)
         # audio (:352-363)
-        feats = frontends.feature_extractor(self.wav2vec2, audio_features)
+        feats = frontends.feature_extractor_cl(self.wav2vec2, audio_features)    # channels-last [B, frames, C]
         if audio_mask is not None:
-            audio_mask = self._get_feature_vector_attention_mask(feats.shape[2], audio_mask, add_adapter=False)
-        embedded_audio, _ = self.wav2vec2.feature_projection(feats.transpose(1, 2))
+            audio_mask = self._get_feature_vector_attention_mask(feats.shape[1], audio_mask, add_adapter=False)
+        embedded_audio, _ = self.wav2vec2.feature_projection(feats)
         embedded_audio = self._mask_hidden_states(embedded_audio, audio_mask, train)
         enc = self.wav2vec2.encoder
         embedded_audio = embedded_audio + frontends.pos_conv_embed(enc.pos_conv_embed, embedded_audio)

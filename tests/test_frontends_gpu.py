@@ -68,3 +68,33 @@ def test_positional_conv_matches_hf(hidden, T):
     assert rel(xo.grad, xr.grad) < 1e-2
     for k, p in pc.named_parameters():
         assert rel(p.grad, ref_grads[k]) < 1.5e-2, k
+
+
+@pytest.mark.parametrize("B,L", [(2, 16000), (3, 48000), (1, 4000)])
+def test_conv_feature_encoder_matches_hf(B, L):
+    """wav2vec2-base feature encoder (group-norm family) on the kernel path vs the HF module in fp32: output and every
+    parameter gradient.  bf16 activations/operands with fp32 accumulation through 7 layers -> 2e-2 relative-L2."""
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+
+    from multi_modal_emotion_b200 import frontends, synthetic as syn
+
+    torch.manual_seed(0)
+    m = Wav2Vec2Model(Wav2Vec2Config(num_hidden_layers=1)).cuda().eval()
+    m.load_state_dict({k: v.cuda() for k, v in syn.synth_state_dict(m, seed=9).items()})
+    g = torch.Generator().manual_seed(3)
+    wav = torch.randn(B, L, generator=g).cuda()
+    ref = m.feature_extractor(wav).transpose(1, 2)            # [B, T, C]
+    probe = torch.randn(ref.shape, generator=g).cuda()
+    (ref * probe).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in m.feature_extractor.named_parameters()}
+    m.zero_grad()
+    T, R = frontends._fe_rows(L, m.config.conv_kernel, m.config.conv_stride)
+    assert T[-1] == ref.shape[1] and all(r >= t for r, t in zip(R, T))
+    assert all(R[i - 1] == m.config.conv_stride[i] * R[i] for i in range(1, len(R)))
+    out = frontends.feature_extractor_cl(m, wav)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel(out, ref) < 2e-2
+    (out * probe).sum().backward()
+    for k, p in m.feature_extractor.named_parameters():
+        assert p.grad is not None, k
+        assert rel(p.grad, ref_grads[k]) < 3e-2, (k, rel(p.grad, ref_grads[k]))
