@@ -77,8 +77,26 @@ typedef struct tavk_gemm_args {
     int32_t epilogue;                                    /* TAVK_EPI_*                                           */
     int32_t accumulate;                                  /* 1: out += result (f32 out, red.global.add)           */
     int32_t k_splits;                                    /* >=1; >1 requires accumulate                          */
-    int32_t block_n;                                     /* 0 = heuristic, or force 128 / 256                    */
+    int32_t block_n;                                     /* 0 = heuristic, or force 64 / 128 / 256               */
     float alpha;
+    /* ---- grouped / convolution-walk extension (all zero = one plain GEMM) ----
+     * `groups` > 1 runs that many independent [M,N,K] problems in one launch over the SAME two tensor maps; group g
+     * shifts the TMA coordinates by g*a_g_mn / g*a_g_k (A: row-or-mn coordinate, k coordinate), g*b_g_mn / g*b_g_k
+     * (B) and writes its [M,N] block at rows +g*out_g_row, columns +g*out_g_col of out/out2/resid/aux (bias and colsum
+     * are indexed by the output column).
+     * a_kstep (K-major A): elements between consecutive 64-wide k-blocks (0 = 64).  With a_kstep = lda a k-block is
+     * "the next row": a sliding-window (stride-1) convolution tap walk over channels-last activations.
+     * b_box_k_shift (MN-major B): every 64-wide box of the N extent uses the same mn coordinate and k coordinate
+     * + (box index)*shift: the wgrad of that convolution (box = tap).
+     * a_rows/a_cols/b_rows/b_cols: extents of the row-major matrices the tensor maps describe (0 = derived from
+     * M, N, K); cols may exceed ld (overlapping rows).  The strided Conv1d layers of the Wav2Vec2 feature encoder
+     * are plain GEMMs with lda = stride*C, K = kernel*C.  See multi-modal-emotion_b200/frontends.py. */
+    int32_t groups;
+    int32_t a_kstep;
+    int32_t a_g_mn, a_g_k, b_g_mn, b_g_k;
+    int32_t b_box_k_shift;
+    int32_t out_g_row, out_g_col;
+    int64_t a_rows, a_cols, b_rows, b_cols;
 } tavk_gemm_args;
 int tavk_gemm_bf16(const tavk_gemm_args* args, void* stream);
 

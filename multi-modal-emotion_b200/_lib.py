@@ -35,6 +35,10 @@ class GemmArgs(C.Structure):
         ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("accumulate", C.c_int32), ("k_splits", C.c_int32), ("block_n", C.c_int32),
         ("alpha", C.c_float),
+        ("groups", C.c_int32), ("a_kstep", C.c_int32),
+        ("a_g_mn", C.c_int32), ("a_g_k", C.c_int32), ("b_g_mn", C.c_int32), ("b_g_k", C.c_int32),
+        ("b_box_k_shift", C.c_int32), ("out_g_row", C.c_int32), ("out_g_col", C.c_int32),
+        ("a_rows", C.c_int64), ("a_cols", C.c_int64), ("b_rows", C.c_int64), ("b_cols", C.c_int64),
     ]
 
 
@@ -149,15 +153,24 @@ def require_device():
 
 
 # ------------------------------------------------------------------------------------------------ typed wrappers
+_GEMM_EXT = ("groups", "a_kstep", "a_g_mn", "a_g_k", "b_g_mn", "b_g_k", "b_box_k_shift", "out_g_row", "out_g_col",
+             "a_rows", "a_cols", "b_rows", "b_cols")
+
+
 def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2=None, bias=None, resid=None,
          rowbias=None, rows_per_group=0, aux=None, colsum=None, epilogue=EPI_LINEAR, accumulate=False, k_splits=1,
-         block_n=0, alpha=1.0):
-    """out[M,N] = epi(alpha * A·B^T).  A/B bf16 2-D tensors (or views); K-major: [rows,K]; MN-major: [K,rows]."""
+         block_n=0, alpha=1.0, ldo=None, **ext):
+    """out[M,N] = epi(alpha * A·B^T).  A/B bf16 2-D tensors (or views); K-major: [rows,K]; MN-major: [K,rows].
+    ``ext``: the grouped / convolution-walk fields of tavk_gemm_args (groups, a_kstep, a_g_mn, ..., b_cols)."""
     a = GemmArgs()
+    for k, v in ext.items():
+        if k not in _GEMM_EXT:
+            raise TypeError("gemm() got an unexpected keyword argument %r" % k)
+        setattr(a, k, int(v))
     a.A, a.lda, a.a_mn_major = A.data_ptr(), (lda if lda is not None else A.stride(0)), int(a_mn)
     a.B, a.ldb, a.b_mn_major = B.data_ptr(), (ldb if ldb is not None else B.stride(0)), int(b_mn)
     a.M, a.N, a.K = M, N, K
-    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.out, a.ldo = out.data_ptr(), (ldo if ldo is not None else out.stride(0))
     a.out_dtype = BF16 if out.dtype == torch.bfloat16 else F32
     a.out2, a.ldo2 = _ptr(out2), (out2.stride(0) if out2 is not None else 0)
     a.bias = _ptr(bias)

@@ -27,11 +27,11 @@ constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
 
 template <int BLOCK_N>
 struct GemmCfg {
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (256 or 512 columns)
+    static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (128, 256 or 512 columns)
     static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // one 32x32 fp32 transpose patch per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -52,6 +52,12 @@ struct GemmDev {
     const __nv_bfloat16* aux;
     long long ldaux;
     float* colsum;
+    // grouped / convolution-walk generalisation (defaults: groups = 1, a_kstep = 64, offsets 0, b_box_mn_step = 64)
+    int groups, tiles_per_group;
+    int a_kstep;                    // K-major A: k-coordinate advance per k-block (a conv tap walk uses the row pitch)
+    int a_g_mn, a_g_k, b_g_mn, b_g_k;   // per-group offsets of the TMA coordinates
+    int b_box_mn_step, b_box_k_shift;   // MN-major B: per 64-wide box j of a tile: mn += step, k += shift * (global box)
+    int out_g_row, out_g_col;       // per-group offset of the output block (also bias / colsum / resid / aux columns)
     int epilogue;
     int accumulate;
     float alpha;
@@ -67,8 +73,9 @@ struct GemmDev {
 // ahead (across tile boundaries too) in two register buffers, and the per-row work is branch-free (predicated loads
 // and stores only) so the 16 independent GELU polynomial chains of a chunk interleave.
 struct EpiItem {
-    int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns
-    bool col_ok, lead;      // column group inside N; first K-split (applies bias / row-bias / residual)
+    int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns (global output coordinates)
+    int rows_valid;         // how many of the 32 rows lie inside the (group's) M
+    bool col_ok, lead;      // column group inside the (group's) N; first K-split (applies bias / row-bias / residual)
 };
 
 enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_RED = 2 };   // plain fp32 store | bf16 store | fp32 red.global.add (split-K / +=)
@@ -90,8 +97,7 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
         const float* rp = p.resid + (long long)(w.row_base + rsub) * p.ldr + w.col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = w.row_base + i * 4 + rsub;
-            const bool ok = row < p.M && w.col_ok;
+            const bool ok = (i * 4 + rsub) < w.rows_valid && w.col_ok;
             o.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (use_res && ok) o.res[i] = ld_global_nc_v4(rp + (long long)i * 4 * p.ldr);
         }
@@ -99,7 +105,7 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = w.row_base + i * 4 + rsub;
-                if (row < p.M && w.col_ok) {
+                if ((i * 4 + rsub) < w.rows_valid && w.col_ok) {
                     const float4 q4 = __ldg(reinterpret_cast<const float4*>(
                         p.rowbias + (long long)(row / p.rows_per_group) * p.N + w.col));
                     o.res[i].x += q4.x; o.res[i].y += q4.y; o.res[i].z += q4.z; o.res[i].w += q4.w;
@@ -111,9 +117,8 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
         const __nv_bfloat16* ap = p.aux + (long long)(w.row_base + rsub) * p.ldaux + w.col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = w.row_base + i * 4 + rsub;
             o.aux[i] = make_uint2(0u, 0u);
-            if (row < p.M && w.col_ok) o.aux[i] = ld_global_nc_v2(ap + (long long)i * 4 * p.ldaux);
+            if ((i * 4 + rsub) < w.rows_valid && w.col_ok) o.aux[i] = ld_global_nc_v2(ap + (long long)i * 4 * p.ldaux);
         }
     }
 }
@@ -151,7 +156,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rl = i * 4 + rsub;
-        const bool ok = (w.row_base + rl) < p.M && w.col_ok;
+        const bool ok = rl < w.rows_valid && w.col_ok;
         float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
         unpk(fma2(pk(v.x, v.y), alpha2, blo), v.x, v.y);
         unpk(fma2(pk(v.z, v.w), alpha2, bhi), v.z, v.w);
@@ -217,46 +222,54 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
 template <int BLOCK_N, int MODE, int OUT>
 TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t stg, int lane, int quarter, int half,
                                int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
-    constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (2 or 4: always even)
+    constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     const int cc = lane & 7, rsub = lane >> 3;
     auto item = [&](int tile, int ci) {
         EpiItem w;
-        const int mn = tile / p.k_splits;
-        w.lead = (tile % p.k_splits) == 0;
-        w.row_base = (mn / p.num_n_blocks) * kBlockM + quarter * 32;
-        w.col = (mn % p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32 + cc * 4;
-        w.col_ok = w.col < p.N;             // N % 8 == 0: a 4-column group is in or out as a whole
+        const int g = tile / p.tiles_per_group;
+        const int tg = tile - g * p.tiles_per_group;
+        const int mn = tg / p.k_splits;
+        const int row_local = (mn / p.num_n_blocks) * kBlockM + quarter * 32;
+        const int col_local = (mn % p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32 + cc * 4;
+        w.lead = (tg % p.k_splits) == 0;
+        w.rows_valid = p.M - row_local;
+        w.row_base = g * p.out_g_row + row_local;
+        w.col = g * p.out_g_col + col_local;
+        w.col_ok = col_local < p.N;         // N % 8 == 0: a 4-column group is in or out as a whole
         return w;
     };
+    // The work of this warp is the flat sequence of (tile, chunk) items; the global operands of item i+1 are
+    // requested before item i is processed, alternating between two register buffers.
     EpiOperands<MODE> opA, opB;
     EpiItem wA, wB;
-    int tile = blockIdx.x;
-    if (tile < num_tiles) {
-        wA = item(tile, 0);
-        epi_issue_loads<MODE>(p, wA, rsub, opA);
-    }
-    int it = 0;
-    for (; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 32);
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int ci = 0; ci < kPer; ci += 2) {
-            wB = item(tile, ci + 1);
-            epi_issue_loads<MODE>(p, wB, rsub, opB);
-            epi_process<MODE, OUT>(p, wA, opA, tacc + (uint32_t)(ci * 64), stg, lane, nullptr);
-            // next item for buffer A: two chunks on in this tile, or the first chunk of the CTA's next tile
-            const bool last = (ci + 2 >= kPer);
-            const int ntile = last ? tile + (int)gridDim.x : tile;
-            if (ntile < num_tiles) {
-                wA = item(ntile, last ? 0 : ci + 2);
-                epi_issue_loads<MODE>(p, wA, rsub, opA);
-            }
-            epi_process<MODE, OUT>(p, wB, opB, tacc + (uint32_t)((ci + 1) * 64), stg, lane,
-                                   last ? &tmem_empty_bar[acc] : nullptr);
+    int tile = blockIdx.x, ci = 0, it = 0;
+    if (tile >= num_tiles) return;
+    wA = item(tile, 0);
+    epi_issue_loads<MODE>(p, wA, rsub, opA);
+    auto step = [&](const EpiItem& w_cur, const EpiOperands<MODE>& op_cur, EpiItem& w_nxt, EpiOperands<MODE>& op_nxt) {
+        int ntile = tile, nci = ci + 1;
+        if (nci == kPer) { nci = 0; ntile += (int)gridDim.x; }
+        const bool more = ntile < num_tiles;
+        if (more) {
+            w_nxt = item(ntile, nci);
+            epi_issue_loads<MODE>(p, w_nxt, rsub, op_nxt);
         }
+        const int acc = it & 1;
+        if (ci == 0) {
+            mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + (half + 2 * ci) * 32);
+        const bool last = (ci == kPer - 1);
+        epi_process<MODE, OUT>(p, w_cur, op_cur, taddr, stg, lane, last ? &tmem_empty_bar[acc] : nullptr);
+        if (last) ++it;
+        tile = ntile; ci = nci;
+        return more;
+    };
+#pragma unroll 1
+    while (true) {
+        if (!step(wA, opA, wB, opB)) break;
+        if (!step(wB, opB, wA, opA)) break;
     }
 }
 
@@ -300,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
+    const int num_tiles = p.groups * p.tiles_per_group;
 
     if (warp_idx == 0) {
         // ===================== TMA producer (one thread) =====================
@@ -308,12 +321,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int split = tile % p.k_splits;
-                const int mn = tile / p.k_splits;
+                const int g = tile / p.tiles_per_group;
+                const int tg = tile - g * p.tiles_per_group;
+                const int split = tg % p.k_splits;
+                const int mn = tg / p.k_splits;
                 const int n_blk = mn % p.num_n_blocks;
                 const int m_blk = mn / p.num_n_blocks;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                const int a_mn0 = m_blk * kBlockM + g * p.a_g_mn, a_k0 = g * p.a_g_k;
+                const int b_k0 = g * p.b_g_k;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -322,18 +339,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if constexpr (A_MN) {
 #pragma unroll
                         for (int j = 0; j < kBlockM / 64; ++j)
-                            tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m_blk * kBlockM + j * 64,
-                                        kb * kBlockK);
+                            tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], a_mn0 + j * 64, a_k0 + kb * kBlockK);
                     } else {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], a_k0 + kb * p.a_kstep, a_mn0);
                     }
                     if constexpr (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_N / 64; ++j)
-                            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n_blk * BLOCK_N + j * 64,
-                                        kb * kBlockK);
+                        for (int j = 0; j < BLOCK_N / 64; ++j) {
+                            const int box = n_blk * (BLOCK_N / 64) + j;
+                            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], box * p.b_box_mn_step + g * p.b_g_mn,
+                                        b_k0 + kb * kBlockK + box * p.b_box_k_shift);
+                        }
                     } else {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], b_k0 + kb * kBlockK, n_blk * BLOCK_N + g * p.b_g_mn);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -351,7 +369,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         uint32_t phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int split = tile % p.k_splits;
+            const int split = (tile % p.tiles_per_group) % p.k_splits;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
             const int acc = it & 1;
@@ -475,16 +493,22 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     const int vec = (a->out_dtype == TAVK_BF16) ? 8 : 4;
     TAVK_CHECK(a->ldo % vec == 0, 1, "tavk_gemm_bf16: ldo must be a multiple of %d", vec);
 
-    // tile-shape heuristic: prefer 128x256 unless 128x128 fills the SMs noticeably better
+    const int groups = a->groups > 1 ? a->groups : 1;
+    TAVK_CHECK(a->b_box_k_shift == 0 || a->b_mn_major, 1, "tavk_gemm_bf16: b_box_k_shift needs an MN-major B operand");
+    TAVK_CHECK(a->a_kstep == 0 || (!a->a_mn_major && a->a_kstep % 8 == 0), 1,
+               "tavk_gemm_bf16: a_kstep needs a K-major A operand and a multiple of 8 elements");
+
+    // tile-shape heuristic: the widest tile whose wave quantisation is not noticeably worse than a narrower one's
     const int sms = sm_count();
     const int mblocks = (a->M + kBlockM - 1) / kBlockM;
     auto waves_eff = [&](int bn) {
-        const long long tiles = (long long)mblocks * ((a->N + bn - 1) / bn) * k_splits;
+        const long long tiles = (long long)groups * mblocks * ((a->N + bn - 1) / bn) * k_splits;
         const long long waves = (tiles + sms - 1) / sms;
         return (double)tiles / (double)(waves * sms);
     };
     int block_n = 256;
-    if (a->block_n == 128 || a->block_n == 256) block_n = a->block_n;
+    if (a->block_n == 64 || a->block_n == 128 || a->block_n == 256) block_n = a->block_n;
+    else if (a->N <= 64) block_n = 64;
     else if (a->N <= 128 || waves_eff(128) > waves_eff(256) * 1.15) block_n = 128;
 
     GemmDev d;
@@ -502,17 +526,30 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     d.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); d.ldaux = a->ldaux;
     d.colsum = a->colsum;
     d.epilogue = a->epilogue; d.accumulate = a->accumulate; d.alpha = a->alpha;
+    d.groups = groups;
+    d.tiles_per_group = d.num_m_blocks * d.num_n_blocks * d.k_splits;
+    d.a_kstep = a->a_kstep > 0 ? a->a_kstep : kBlockK;
+    d.a_g_mn = a->a_g_mn; d.a_g_k = a->a_g_k; d.b_g_mn = a->b_g_mn; d.b_g_k = a->b_g_k;
+    d.b_box_k_shift = a->b_box_k_shift;
+    d.b_box_mn_step = a->b_box_k_shift != 0 ? 0 : 64;
+    d.out_g_row = a->out_g_row; d.out_g_col = a->out_g_col;
 
+    // tensor maps over the row-major matrices in memory ([rows, cols], pitch ld); explicit extents let a caller
+    // describe overlapping rows (cols > ld: strided / sliding-window convolutions) and grouped problems
     CUtensorMap ta, tb;
     int rc;
-    if (a->a_mn_major) rc = make_tmap_bf16(&ta, a->A, a->K, a->M, a->lda, 64, kBlockK);
-    else               rc = make_tmap_bf16(&ta, a->A, a->M, a->K, a->lda, kBlockK, kBlockM);
+    const long long a_rows = a->a_rows > 0 ? a->a_rows : (a->a_mn_major ? a->K : a->M);
+    const long long a_cols = a->a_cols > 0 ? a->a_cols : (a->a_mn_major ? a->M : a->K);
+    const long long b_rows = a->b_rows > 0 ? a->b_rows : (a->b_mn_major ? a->K : a->N);
+    const long long b_cols = a->b_cols > 0 ? a->b_cols : (a->b_mn_major ? a->N : a->K);
+    if (a->a_mn_major) rc = make_tmap_bf16(&ta, a->A, a_rows, a_cols, a->lda, 64, kBlockK);
+    else               rc = make_tmap_bf16(&ta, a->A, a_rows, a_cols, a->lda, kBlockK, kBlockM);
     if (rc) return rc;
-    if (a->b_mn_major) rc = make_tmap_bf16(&tb, a->B, a->K, a->N, a->ldb, 64, kBlockK);
-    else               rc = make_tmap_bf16(&tb, a->B, a->N, a->K, a->ldb, kBlockK, block_n);
+    if (a->b_mn_major) rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, 64, kBlockK);
+    else               rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, kBlockK, block_n);
     if (rc) return rc;
 
-    const long long tiles = (long long)d.num_m_blocks * d.num_n_blocks * d.k_splits;
+    const long long tiles = (long long)d.groups * d.tiles_per_group;
     const int grid = (int)(tiles < sms ? tiles : sms);
 #define TAVK_GEMM_DISPATCH(BN)                                                                   \
     if (a->a_mn_major && a->b_mn_major) return launch_gemm<BN, true, true>(ta, tb, d, grid, stream);   \
@@ -520,6 +557,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN, false, true>(ta, tb, d, grid, stream); \
     return launch_gemm<BN, false, false>(ta, tb, d, grid, stream);
     if (block_n == 256) { TAVK_GEMM_DISPATCH(256) }
-    TAVK_GEMM_DISPATCH(128)
+    if (block_n == 128) { TAVK_GEMM_DISPATCH(128) }
+    TAVK_GEMM_DISPATCH(64)
 #undef TAVK_GEMM_DISPATCH
 }

@@ -226,25 +226,30 @@ def video_embeddings(emb, pixel_values, bool_masked_pos, keep_count=None):
 
 
 # ------------------------------------------------------------------------------------------------ positional conv
-def _windows_bf16(x_bf, k, left, right):
-    """x_bf [B,T,H] bf16 -> sliding-window matrix [B*T, H*k] with column order (channel, tap): window t covers padded
-    rows t .. t+k-1."""
+def _pad_rows_bf16(x_bf, left, Tp, tail):
+    """x_bf [B,T,H] bf16 -> zero-padded [B*Tp + tail, H]: sample b occupies rows b*Tp + left .. b*Tp + left + T - 1."""
     B, T, H = x_bf.shape
-    xp = F.pad(x_bf, (0, 0, left, right))
-    win = xp.unfold(1, k, 1)[:, :T]          # [B, T, H, k] view
-    out = torch.empty((B, T, H, k), dtype=torch.bfloat16, device=x_bf.device)
-    out.copy_(win)
-    return out.view(B * T, H * k)
+    buf = torch.zeros((B * Tp + tail, H), dtype=torch.bfloat16, device=x_bf.device)
+    buf[:B * Tp].view(B, Tp, H)[:, left:left + T].copy_(x_bf)
+    return buf
 
 
-def _grouped_gemm(cols, w_bf, bias, M, H, G, k):
-    """out[:, g*Cg:(g+1)*Cg] = cols[:, g*Cg*k:(g+1)*Cg*k] @ w_bf[g*Cg:(g+1)*Cg]^T (+ bias)."""
-    Cg = H // G
-    Kg = Cg * k
-    out = torch.empty((M, H), dtype=torch.float32, device=cols.device)
-    for g in range(G):
-        L.gemm(cols[:, g * Kg:(g + 1) * Kg], w_bf[g * Cg:(g + 1) * Cg], out[:, g * Cg:(g + 1) * Cg], M=M, N=Cg, K=Kg,
-               lda=H * k, ldb=Kg, bias=None if bias is None else bias[g * Cg:(g + 1) * Cg])
+def _pack_taps_bf16(w, Cg, k):
+    """conv weight [H, Cg, k] -> bf16 [H, k*64] with column (tap, ic) and zeros for ic >= Cg: one 64-wide k-block
+    per tap, so a k-block of the GEMM is a TMA box of 64 channels of one (shifted) activation row."""
+    H = w.shape[0]
+    wp = torch.zeros((H, k, 64), dtype=torch.bfloat16, device=w.device)
+    wp[:, :, :Cg].copy_(w.permute(0, 2, 1))
+    return wp.view(H, k * 64)
+
+
+def _sliding_conv(xpad, wp, bias, rows, H, G, Cg, k):
+    """out[m, g*Cg + oc] = sum_tap sum_ic xpad[m + tap, g*Cg + ic] * wp[g*Cg + oc, tap*64 + ic]   (m < rows): an
+    implicit GEMM — the k-block walk of the A operand steps one activation ROW per tap (a_kstep = row pitch), the 16
+    groups are 16 problems of one launch; nothing like an im2col matrix is ever written."""
+    out = torch.empty((rows, H), dtype=torch.float32, device=xpad.device)
+    L.gemm(xpad, wp, out, M=rows, N=Cg, K=k * 64, lda=H, ldb=k * 64, bias=bias, groups=G, a_kstep=H, a_g_k=Cg,
+           b_g_mn=Cg, out_g_col=Cg, a_rows=rows, a_cols=k * H, b_rows=H, b_cols=k * 64)
     return out
 
 
@@ -255,41 +260,54 @@ class _GroupedConv1dSameFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, groups):
         B, T, H = x.shape
         Cg, k = weight.shape[1], weight.shape[2]
+        if Cg > 64 or Cg % 8 != 0:
+            raise NotImplementedError("positional conv: at most 64 channels per group, multiple of 8 (got %d)" % Cg)
+        Tp = T + k
         x_bf = L.cast_bf16(x.contiguous().float())
-        cols = _windows_bf16(x_bf, k, k // 2, k // 2)
-        w_bf = L.cast_bf16(weight.detach().reshape(H, Cg * k))
-        y = _grouped_gemm(cols, w_bf, bias, B * T, H, groups, k)
-        ctx.save_for_backward(x_bf, weight)
+        xpad = _pad_rows_bf16(x_bf, k // 2, Tp, k)
+        y = _sliding_conv(xpad, _pack_taps_bf16(weight.detach(), Cg, k), bias, B * Tp, H, groups, Cg, k)
+        ctx.save_for_backward(xpad, weight)
         ctx.meta = (B, T, H, Cg, k, groups, bias is not None)
-        return y.view(B, T, H)
+        return y.view(B, Tp, H)[:, :T].contiguous()
 
     @staticmethod
     def backward(ctx, dy):
-        x_bf, weight = ctx.saved_tensors
+        xpad, weight = ctx.saved_tensors
         B, T, H, Cg, k, G, has_bias = ctx.meta
-        M = B * T
-        dy = dy.contiguous().float().view(M, H)
-        dy_bf = L.cast_bf16(dy)
+        Tp = T + k
+        dy = dy.contiguous().float()
         db = None
         if has_bias:
             db = torch.empty((H,), dtype=torch.float32, device=dy.device)
-            L.colsum(dy, db, M=M, N=H)
-        # wgrad: dW_g[oc, (ic,k)] = sum_m dY[m, g*Cg+oc] * cols[m, g*Cg*k + (ic,k)]   (window matrix recomputed)
-        cols = _windows_bf16(x_bf, k, k // 2, k // 2)
-        dw = torch.zeros((H, Cg * k), dtype=torch.float32, device=dy.device)
-        Kg = Cg * k
-        ks = max(1, min(148 // ((Kg + 255) // 256), (M + 511) // 512))
-        for g in range(G):
-            L.gemm(dy_bf[:, g * Cg:(g + 1) * Cg], cols[:, g * Kg:(g + 1) * Kg], dw[g * Cg:(g + 1) * Cg], M=Cg, N=Kg, K=M,
-                   lda=H, ldb=H * k, a_mn=True, b_mn=True, accumulate=True, k_splits=ks)
-        del cols
+            L.colsum(dy.view(B * T, H), db, M=B * T, N=H)
+        left = k // 2 - 1
+        dypad = _pad_rows_bf16(L.cast_bf16(dy), left, Tp, k)
+        # wgrad: dW[g*Cg+oc, ic, tap] = sum_m dY[m, g*Cg+oc] * xpad[m + tap, g*Cg+ic]  (m over the padded row grid, where
+        # dY rows are zero outside the T valid frames): A = dY (MN-major), B = xpad (MN-major), one 64-wide box of N per
+        # tap reading rows shifted by the tap (b_box_k_shift = 1); output [H, k*64] regrouped to [H, Cg, k] afterwards.
+        dwt = torch.zeros((H, k * 64), dtype=torch.float32, device=dy.device)
+        rows = B * Tp
+        ks = max(1, min(4, 148 * 2 // (G * (k * 64 // 256))))
+        L.gemm(dypad[left:], xpad, dwt, M=Cg, N=k * 64, K=rows, lda=H, ldb=H, a_mn=True, b_mn=True, accumulate=True,
+               k_splits=ks, groups=G, a_g_mn=Cg, b_g_mn=Cg, b_box_k_shift=1, out_g_row=Cg, a_rows=rows, a_cols=H,
+               b_rows=rows + k, b_cols=H)
+        dw = dwt.view(H, k, 64)[:, :, :Cg].permute(0, 2, 1)
         # dgrad: dX[s] = sum_u dYpad[s+u] · W[.., k-1-u] with dYpad shifted by k/2-1 -> same routine, flipped taps and
         # (oc, ic) transposed inside every group
-        wf = weight.detach().view(G, Cg, Cg, k).flip(-1).transpose(1, 2).reshape(H, Cg * k)
-        wf_bf = L.cast_bf16(wf.contiguous())
-        dcols = _windows_bf16(dy_bf.view(B, T, H), k, k // 2 - 1, k // 2)
-        dx = _grouped_gemm(dcols, wf_bf, None, M, H, G, k)
-        return dx.view(B, T, H), dw.view(H, Cg, k), db, None
+        wf = weight.detach().view(G, Cg, Cg, k).flip(-1).transpose(1, 2).reshape(H, Cg, k)
+        dx = _sliding_conv(dypad, _pack_taps_bf16(wf, Cg, k), None, rows, H, G, Cg, k)
+        return dx.view(B, Tp, H)[:, :T].contiguous(), dw, db, None
+
+
+def _weight_normed(conv):
+    """weight = g * v / ||v|| (norm over all dims but `dim`) from the parametrization's own tensors with plain torch
+    ops (autograd differentiates them): avoids ATen's slow last-dim weight_norm kernels on the 768x48x128 weight."""
+    par = getattr(conv, "parametrizations", None)
+    if par is None or not hasattr(par, "weight"):
+        return conv.weight
+    g, v = par.weight.original0, par.weight.original1
+    dims = [d for d in range(v.dim()) if g.shape[d] == 1]
+    return v * (g / v.pow(2).sum(dim=dims, keepdim=True).sqrt())
 
 
 def pos_conv_embed(pc, hidden):
@@ -298,5 +316,5 @@ def pos_conv_embed(pc, hidden):
     k = conv.kernel_size[0]
     if k % 2 != 0 or conv.padding[0] != k // 2 or conv.stride[0] != 1 or conv.dilation[0] != 1:
         raise NotImplementedError("positional conv: even kernel with padding k/2 expected")
-    y = _GroupedConv1dSameFn.apply(hidden, conv.weight, conv.bias, conv.groups)
+    y = _GroupedConv1dSameFn.apply(hidden, _weight_normed(conv), conv.bias, conv.groups)
     return F.gelu(y)
