@@ -193,16 +193,21 @@ int tavk_permute_bshd_bhds(const void* in, void* out, int B, int S, int nh, int 
  * per sample (rows t >= T are zero); the layers after it run on tavk_gemm_bf16 with lda = stride*C (overlapping TMA
  * rows), see multi-modal-emotion_b200/frontends.py.
  *   conv0_fwd           : u[b,t,c] = sum_j wav[b, s*t+j] w[c,j] (+bias[c])          wav f32 [B,L], w f32 [C,k]
- *   groupnorm_gelu_fwd  : per (b,c) mean/rstd over t < T (two-pass, f32); z = gamma*xhat+beta, a = gelu_erf(z)
- *   groupnorm_conv0_bwd : from dz (gradient w.r.t. z, bf16): dgamma, dbeta, dw[C,k] (and dbias) are ACCUMULATED
- *                         (atomics; zero them first); the waveform needs no gradient. */
+ *   groupnorm_gelu_fwd  : per (b,c) mean/rstd over t < T (shifted one-pass sums, f32); z = gamma*xhat+beta,
+ *                         a = gelu_erf(z); sums_ws: f32 [B,2,C] workspace
+ *   groupnorm_bwd       : from dz (gradient w.r.t. z, bf16): du = gamma*rstd*(dz - mean_t dz - xhat*mean_t(dz*xhat))
+ *                         (bf16, may alias dz; zero in the padding rows) and sums_ws[b,0,c] = sum_t dz (-> dbeta),
+ *                         sums_ws[b,1,c] = sum_t dz*xhat (-> dgamma)
+ *   wave_windows        : win[b*R+t, j] = bf16(wav[b, s*t+j]) (j < k, else 0), bf16 [B*R, 16]: with it the conv0 weight
+ *                         gradient is the wgrad GEMM du^T x win; the waveform needs no gradient. */
 int tavk_conv0_fwd(const float* wav, const float* w, const float* bias, void* u_bf16, int B, int L, int R, int T, int C,
                    int k, int s, void* stream);
 int tavk_groupnorm_gelu_fwd(const void* u_bf16, const float* gamma, const float* beta, void* z_bf16, void* a_bf16,
-                            float* mean, float* rstd, int B, int R, int T, int C, float eps, void* stream);
-int tavk_groupnorm_conv0_bwd(const void* dz_bf16, const void* u_bf16, const float* mean, const float* rstd,
-                             const float* gamma, const float* wav, float* dgamma, float* dbeta, float* dw, float* dbias,
-                             int B, int L, int R, int T, int C, int k, int s, void* stream);
+                            float* mean, float* rstd, float* sums_ws, int B, int R, int T, int C, float eps,
+                            void* stream);
+int tavk_groupnorm_bwd(const void* dz_bf16, const void* u_bf16, const float* mean, const float* rstd,
+                       const float* gamma, void* du_bf16, float* sums_ws, int B, int R, int T, int C, void* stream);
+int tavk_wave_windows(const float* wav, void* win_bf16, int B, int L, int R, int T, int k, int s, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Weighted softmax cross-entropy (utils/global_functions.py:63-64,76,83 — nn.CrossEntropyLoss(weight=w), mean).

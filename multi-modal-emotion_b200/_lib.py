@@ -90,8 +90,9 @@ SIGNATURES = {
     "tavk_dropout_bwd": [_P, _P, _P, _L, _F, _P],
     "tavk_permute_bshd_bhds": [_P, _P, _I, _I, _I, _I, _I, _P],
     "tavk_conv0_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "tavk_groupnorm_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
-    "tavk_groupnorm_conv0_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tavk_groupnorm_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tavk_groupnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tavk_wave_windows": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tavk_softmax_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_softmax_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_grad_sqnorm": [_P, _L, _P, _P],
@@ -105,7 +106,7 @@ kernel_count = 0   # CUDA kernels those entry points launched (bench.py reports 
 record_gemms = False
 gemm_log = []      # (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, rowbias, accumulate, k_splits) per launch
 # kernels launched per entry point (memset nodes are not counted)
-_KERNELS = {"tavk_attn_bwd": 3}
+_KERNELS = {"tavk_attn_bwd": 3, "tavk_groupnorm_gelu_fwd": 2, "tavk_groupnorm_bwd": 2}
 
 
 def lib():

@@ -9,7 +9,7 @@
 // plain tcgen05 GEMM over the whole batch (A row pitch = stride*C, row length k*C: overlapping TMA rows).  Rows
 // t >= T of a sample are padding: written as zeros here, and they never feed a valid output downstream.
 //
-// All three kernels are HBM/L2-bound streaming passes (C_in = 1: 2*k FLOP per output element).
+// All kernels here are HBM/L2-bound streaming passes (C_in = 1: 2*k FLOP per output element).
 #include "../../include/tavk.h"
 #include "common.cuh"
 
@@ -58,140 +58,201 @@ conv0_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ w, con
     }
 }
 
-// One block per (sample b, 16 channels): thread = (row lane 0..31, channel pair 0..7).
-// Pass 1 mean, pass 2 centred variance (two-pass: no E[x^2]-E[x]^2 cancellation), pass 3 z = gamma*xhat + beta (bf16,
-// saved for GELU') and a = GELU(z) (bf16, the next layer's GEMM operand).  The 16-channel slab of one sample
-// (R x 32 B) stays in L2 between the passes.
-constexpr int kGnCh = 16;
-constexpr int kGnLanes = 32;
+// ---- GroupNorm (C groups = per-channel statistics over time) + GELU, and its backward, as streaming passes --------
+// Common shape: grid (C/64, row chunks, B), 256 threads = 32 row lanes x 8 channel octets; every access is a 16-byte
+// (8 x bf16) load/store, 128 contiguous bytes per row per block.  Per-(sample, channel) sums are reduced by warp
+// shuffles, shared memory across the 8 warps, then one fp32 atomic per channel per block.
+constexpr int kGnRowsPerBlock = 512;
 
-TAVK_DEVINL float2 gn_block_reduce2(float2 v, float2* red, int lane, int cp) {
-    red[lane * (kGnCh / 2) + cp] = v;
-    __syncthreads();
-    if (lane == 0) {
-        float2 a = make_float2(0.f, 0.f);
-        for (int i = 0; i < kGnLanes; ++i) {
-            const float2 q = red[i * (kGnCh / 2) + cp];
-            a.x += q.x; a.y += q.y;
-        }
-        red[cp] = a;
-    }
-    __syncthreads();
-    const float2 r = red[cp];
-    __syncthreads();
+struct bf16x8 {
+    float v[8];
+};
+TAVK_DEVINL bf16x8 ld_bf16x8(const __nv_bfloat16* p) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    bf16x8 r;
+    float2 t;
+    t = unpack_bf16x2(q.x); r.v[0] = t.x; r.v[1] = t.y;
+    t = unpack_bf16x2(q.y); r.v[2] = t.x; r.v[3] = t.y;
+    t = unpack_bf16x2(q.z); r.v[4] = t.x; r.v[5] = t.y;
+    t = unpack_bf16x2(q.w); r.v[6] = t.x; r.v[7] = t.y;
     return r;
 }
-
-__global__ void __launch_bounds__(256)
-groupnorm_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ a,
-                          float* __restrict__ mean, float* __restrict__ rstd, int R, int T, int C, float eps) {
-    __shared__ float2 red[kGnLanes * (kGnCh / 2)];
-    const int b = blockIdx.y;
-    const int cp = threadIdx.x & 7, lane = threadIdx.x >> 3;
-    const int c = blockIdx.x * kGnCh + cp * 2;
-    const size_t base = (size_t)b * R * C + c;
-    float2 s = make_float2(0.f, 0.f);
-    for (int t = lane; t < T; t += kGnLanes) {
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(u + base + (size_t)t * C));
-        s.x += v.x; s.y += v.y;
+TAVK_DEVINL void st_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+}
+// acc[2][8] per thread -> out0/out1[c0 + 8*cg + i] += block totals
+TAVK_DEVINL void gn_block_accumulate(float (&a0)[8], float (&a1)[8], float* red, float* out0, float* out1, int c0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = threadIdx.x & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], 8);  a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], 8);
+        a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], 16); a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], 16);
     }
-    s = gn_block_reduce2(s, red, lane, cp);
-    const float m0 = s.x / T, m1 = s.y / T;
-    float2 q = make_float2(0.f, 0.f);
-    for (int t = lane; t < T; t += kGnLanes) {
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(u + base + (size_t)t * C));
-        q.x += (v.x - m0) * (v.x - m0); q.y += (v.y - m1) * (v.y - m1);
-    }
-    q = gn_block_reduce2(q, red, lane, cp);
-    const float r0 = rsqrtf(q.x / T + eps), r1 = rsqrtf(q.y / T + eps);
-    if (lane == 0) {
-        mean[(size_t)b * C + c] = m0; mean[(size_t)b * C + c + 1] = m1;
-        rstd[(size_t)b * C + c] = r0; rstd[(size_t)b * C + c + 1] = r1;
-    }
-    const float g0 = gamma[c] * r0, g1 = gamma[c + 1] * r1;
-    const float o0 = beta[c] - m0 * g0, o1 = beta[c + 1] - m1 * g1;
-    for (int t = lane; t < R; t += kGnLanes) {
-        float z0 = 0.f, z1 = 0.f, a0 = 0.f, a1 = 0.f;
-        if (t < T) {
-            const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(u + base + (size_t)t * C));
-            z0 = fmaf(v.x, g0, o0); z1 = fmaf(v.y, g1, o1);
-            gelu_fast2(z0, z1, a0, a1);
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            red[(warp * 64 + cg * 8 + i) * 2] = a0[i];
+            red[(warp * 64 + cg * 8 + i) * 2 + 1] = a1[i];
         }
-        *reinterpret_cast<uint32_t*>(z + base + (size_t)t * C) = pack_bf16x2(z0, z1);
-        *reinterpret_cast<uint32_t*>(a + base + (size_t)t * C) = pack_bf16x2(a0, a1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            s0 += red[(w * 64 + threadIdx.x) * 2];
+            s1 += red[(w * 64 + threadIdx.x) * 2 + 1];
+        }
+        atomicAdd(out0 + c0 + threadIdx.x, s0);
+        atomicAdd(out1 + c0 + threadIdx.x, s1);
     }
 }
 
-// Backward of GroupNorm + conv0 for dz (gradient w.r.t. the GroupNorm output, i.e. after GELU' was applied by the
-// producing dgrad GEMM epilogue).  Same block shape as the forward.  Pass 1: s1 = sum_t dz, s2 = sum_t dz*xhat
-// (-> dbeta, dgamma).  Pass 2: du = gamma*rstd*(dz - s1/T - xhat*s2/T) and dW[c, j] += sum_t du[t, c]*wav[s*t + j]
-// (accumulated in registers, block-reduced, one atomic per (channel, tap) per block); du itself is never stored.
+// sums[b][0][c] += sum_t (u - k), sums[b][1][c] += sum_t (u - k)^2 with the shift k = u[b, 0, c] (removes the mean's
+// bulk, so the one-pass variance does not cancel)
 __global__ void __launch_bounds__(256)
-groupnorm_conv0_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u,
-                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                           const float* __restrict__ gamma, const float* __restrict__ wav, float* __restrict__ dgamma,
-                           float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dbias, int L, int R,
-                           int T, int C, int k, int s) {
-    __shared__ float2 red[kGnLanes * (kGnCh / 2)];
-    const int b = blockIdx.y;
-    const int cp = threadIdx.x & 7, lane = threadIdx.x >> 3;
-    const int c = blockIdx.x * kGnCh + cp * 2;
+groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__ sums, int R, int T, int C) {
+    __shared__ float red[8 * 64 * 2];
+    const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const __nv_bfloat16* base = u + (size_t)b * R * C + c0 + cg * 8;
+    const bf16x8 k = ld_bf16x8(base);
+    const int t0 = blockIdx.y * kGnRowsPerBlock, t1 = min(t0 + kGnRowsPerBlock, T);
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+#pragma unroll 4
+    for (int t = t0 + rl; t < t1; t += 32) {
+        const bf16x8 x = ld_bf16x8(base + (size_t)t * C);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float d = x.v[i] - k.v[i];
+            s[i] += d;
+            q[i] = fmaf(d, d, q[i]);
+        }
+    }
+    gn_block_accumulate(s, q, red, sums + (size_t)b * 2 * C, sums + (size_t)b * 2 * C + C, c0);
+}
+
+// mean/rstd from the shifted sums, z = gamma*xhat + beta (bf16, kept for GELU'), a = GELU(z) (bf16, next GEMM operand);
+// padding rows t >= T are written as zeros
+__global__ void __launch_bounds__(256)
+groupnorm_gelu_apply_kernel(const __nv_bfloat16* __restrict__ u, const float* __restrict__ sums,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ a, float* __restrict__ mean,
+                            float* __restrict__ rstd, int R, int T, int C, float eps) {
+    const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = c0 + cg * 8;
     const size_t base = (size_t)b * R * C + c;
-    const float m0 = mean[(size_t)b * C + c], m1 = mean[(size_t)b * C + c + 1];
-    const float r0 = rstd[(size_t)b * C + c], r1 = rstd[(size_t)b * C + c + 1];
-    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-    for (int t = lane; t < T; t += kGnLanes) {
-        const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dz + base + (size_t)t * C));
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(u + base + (size_t)t * C));
-        s1.x += g.x; s1.y += g.y;
-        s2.x += g.x * (v.x - m0) * r0; s2.y += g.y * (v.y - m1) * r1;
-    }
-    s1 = gn_block_reduce2(s1, red, lane, cp);
-    s2 = gn_block_reduce2(s2, red, lane, cp);
-    if (lane == 0) {
-        atomicAdd(dbeta + c, s1.x);  atomicAdd(dbeta + c + 1, s1.y);
-        atomicAdd(dgamma + c, s2.x); atomicAdd(dgamma + c + 1, s2.y);
-    }
-    const float k0 = gamma[c] * r0, k1 = gamma[c + 1] * r1;
-    const float a0 = s1.x / T, a1 = s1.y / T, b0 = s2.x / T, b1 = s2.y / T;
-    float acc0[kConv0MaxK], acc1[kConv0MaxK];
+    const bf16x8 k = ld_bf16x8(u + base);
+    float g[8], o[8];
 #pragma unroll
-    for (int j = 0; j < kConv0MaxK; ++j) acc0[j] = acc1[j] = 0.f;
-    float sb0 = 0.f, sb1 = 0.f;
-    const float* wb = wav + (size_t)b * L;
-    for (int t = lane; t < T; t += kGnLanes) {
-        const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dz + base + (size_t)t * C));
-        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(u + base + (size_t)t * C));
-        const float du0 = k0 * (g.x - a0 - (v.x - m0) * r0 * b0);
-        const float du1 = k1 * (g.y - a1 - (v.y - m1) * r1 * b1);
-        sb0 += du0; sb1 += du1;
+    for (int i = 0; i < 8; ++i) {
+        const float sd = sums[(size_t)b * 2 * C + c + i] / T;
+        const float var = fmaxf(sums[(size_t)b * 2 * C + C + c + i] / T - sd * sd, 0.f);
+        const float m = k.v[i] + sd, r = rsqrtf(var + eps);
+        if (blockIdx.y == 0 && rl == 0) { mean[(size_t)b * C + c + i] = m; rstd[(size_t)b * C + c + i] = r; }
+        g[i] = gamma[c + i] * r;
+        o[i] = beta[c + i] - m * g[i];
+    }
+    const int t0 = blockIdx.y * kGnRowsPerBlock, t1 = min(t0 + kGnRowsPerBlock, R);
+#pragma unroll 2
+    for (int t = t0 + rl; t < t1; t += 32) {
+        float zz[8], aa[8];
+        if (t < T) {
+            const bf16x8 x = ld_bf16x8(u + base + (size_t)t * C);
 #pragma unroll
-        for (int j = 0; j < kConv0MaxK; ++j) {
-            if (j < k) {
-                const int idx = t * s + j;
-                const float x = idx < L ? __ldg(wb + idx) : 0.f;
-                acc0[j] = fmaf(du0, x, acc0[j]);
-                acc1[j] = fmaf(du1, x, acc1[j]);
-            }
+            for (int i = 0; i < 8; ++i) zz[i] = fmaf(x.v[i], g[i], o[i]);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) gelu_fast2(zz[i], zz[i + 1], aa[i], aa[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zz[i] = aa[i] = 0.f;
+        }
+        st_bf16x8(z + base + (size_t)t * C, zz);
+        st_bf16x8(a + base + (size_t)t * C, aa);
+    }
+}
+
+// backward pass 1: sums[b][0][c] += sum_t dz, sums[b][1][c] += sum_t dz * xhat
+__global__ void __launch_bounds__(256)
+groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ sums,
+                           int R, int T, int C) {
+    __shared__ float red[8 * 64 * 2];
+    const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = c0 + cg * 8;
+    const size_t base = (size_t)b * R * C + c;
+    float m[8], r[8], s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m[i] = mean[(size_t)b * C + c + i];
+        r[i] = rstd[(size_t)b * C + c + i];
+        s1[i] = s2[i] = 0.f;
+    }
+    const int t0 = blockIdx.y * kGnRowsPerBlock, t1 = min(t0 + kGnRowsPerBlock, T);
+#pragma unroll 4
+    for (int t = t0 + rl; t < t1; t += 32) {
+        const bf16x8 g = ld_bf16x8(dz + base + (size_t)t * C);
+        const bf16x8 x = ld_bf16x8(u + base + (size_t)t * C);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s1[i] += g.v[i];
+            s2[i] = fmaf(g.v[i], (x.v[i] - m[i]) * r[i], s2[i]);
         }
     }
+    gn_block_accumulate(s1, s2, red, sums + (size_t)b * 2 * C, sums + (size_t)b * 2 * C + C, c0);
+}
+
+// backward pass 2: du = gamma*rstd*(dz - s1/T - xhat*s2/T) (bf16; zero in the padding rows): the conv0 weight gradient is
+// then the tcgen05 wgrad GEMM du^T x [waveform windows]
+__global__ void __launch_bounds__(256)
+groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u,
+                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, const float* __restrict__ sums,
+                           __nv_bfloat16* __restrict__ du, int R, int T, int C) {
+    const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = c0 + cg * 8;
+    const size_t base = (size_t)b * R * C + c;
+    float m[8], r[8], kk[8], a1[8], a2[8];
 #pragma unroll
-    for (int j = 0; j < kConv0MaxK; ++j) {
-        if (j < k) {   // uniform
-            const float2 tot = gn_block_reduce2(make_float2(acc0[j], acc1[j]), red, lane, cp);
-            if (lane == 0) {
-                atomicAdd(dw + (size_t)c * k + j, tot.x);
-                atomicAdd(dw + (size_t)(c + 1) * k + j, tot.y);
-            }
-        }
+    for (int i = 0; i < 8; ++i) {
+        m[i] = mean[(size_t)b * C + c + i];
+        r[i] = rstd[(size_t)b * C + c + i];
+        kk[i] = gamma[c + i] * r[i];
+        a1[i] = sums[(size_t)b * 2 * C + c + i] / T;
+        a2[i] = sums[(size_t)b * 2 * C + C + c + i] / T;
     }
-    if (dbias != nullptr) {
-        const float2 tot = gn_block_reduce2(make_float2(sb0, sb1), red, lane, cp);
-        if (lane == 0) {
-            atomicAdd(dbias + c, tot.x);
-            atomicAdd(dbias + c + 1, tot.y);
+    const int t0 = blockIdx.y * kGnRowsPerBlock, t1 = min(t0 + kGnRowsPerBlock, R);
+#pragma unroll 2
+    for (int t = t0 + rl; t < t1; t += 32) {
+        float d[8];
+        if (t < T) {
+            const bf16x8 g = ld_bf16x8(dz + base + (size_t)t * C);
+            const bf16x8 x = ld_bf16x8(u + base + (size_t)t * C);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = kk[i] * (g.v[i] - a1[i] - (x.v[i] - m[i]) * r[i] * a2[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = 0.f;
         }
+        st_bf16x8(du + base + (size_t)t * C, d);
+    }
+}
+
+// win[b*R + t, j] = bf16(wav[b, s*t + j]) for j < k (0 for k <= j < 16 and for rows t >= T): the B operand of the conv0
+// weight-gradient GEMM
+__global__ void wave_windows_kernel(const float* __restrict__ wav, __nv_bfloat16* __restrict__ win, int L, int R, int T,
+                                    int k, int s, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i & 15);
+        const long long row = i >> 4;
+        const int t = (int)(row % R);
+        const long long b = row / R;
+        const int idx = t * s + j;
+        float v = 0.f;
+        if (j < k && t < T && idx < L) v = wav[b * L + idx];
+        win[i] = __float2bfloat16(v);
     }
 }
 
@@ -215,27 +276,45 @@ extern "C" int tavk_conv0_fwd(const float* wav, const float* w, const float* bia
 }
 
 extern "C" int tavk_groupnorm_gelu_fwd(const void* u, const float* gamma, const float* beta, void* z, void* a,
-                                       float* mean, float* rstd, int B, int R, int T, int C, float eps, void* stream) {
-    TAVK_CHECK(u && gamma && beta && z && a && mean && rstd, 1, "tavk_groupnorm_gelu_fwd: null pointer");
-    TAVK_CHECK(C % kGnCh == 0 && R >= T && T > 0 && B > 0, 1, "tavk_groupnorm_gelu_fwd: C %% %d == 0 required (C=%d)", kGnCh, C);
-    dim3 grid(C / kGnCh, B);
-    groupnorm_gelu_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(u), gamma, beta, reinterpret_cast<__nv_bfloat16*>(z),
-        reinterpret_cast<__nv_bfloat16*>(a), mean, rstd, R, T, C, eps);
+                                       float* mean, float* rstd, float* sums_ws, int B, int R, int T, int C, float eps,
+                                       void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    TAVK_CHECK(u && gamma && beta && z && a && mean && rstd && sums_ws, 1, "tavk_groupnorm_gelu_fwd: null pointer");
+    TAVK_CHECK(C % 64 == 0 && R >= T && T > 0 && B > 0, 1, "tavk_groupnorm_gelu_fwd: C %% 64 == 0 required (C=%d)", C);
+    TAVK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * 2 * C * sizeof(float), stream));
+    dim3 g1(C / 64, (T + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B), g2(C / 64, (R + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B);
+    groupnorm_stats_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, R, T, C);
+    groupnorm_gelu_apply_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, gamma, beta,
+                                                        reinterpret_cast<__nv_bfloat16*>(z),
+                                                        reinterpret_cast<__nv_bfloat16*>(a), mean, rstd, R, T, C, eps);
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int tavk_groupnorm_conv0_bwd(const void* dz, const void* u, const float* mean, const float* rstd,
-                                        const float* gamma, const float* wav, float* dgamma, float* dbeta, float* dw,
-                                        float* dbias, int B, int L, int R, int T, int C, int k, int s, void* stream) {
-    TAVK_CHECK(dz && u && mean && rstd && gamma && wav && dgamma && dbeta && dw, 1, "tavk_groupnorm_conv0_bwd: null pointer");
-    TAVK_CHECK(C % kGnCh == 0 && R >= T && T > 0 && B > 0 && k >= 1 && k <= kConv0MaxK, 1,
-               "tavk_groupnorm_conv0_bwd: bad sizes C=%d k=%d", C, k);
-    dim3 grid(C / kGnCh, B);
-    groupnorm_conv0_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dz), reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, gamma, wav,
-        dgamma, dbeta, dw, dbias, L, R, T, C, k, s);
+extern "C" int tavk_groupnorm_bwd(const void* dz, const void* u, const float* mean, const float* rstd,
+                                  const float* gamma, void* du, float* sums_ws, int B, int R, int T, int C,
+                                  void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    TAVK_CHECK(dz && u && mean && rstd && gamma && du && sums_ws, 1, "tavk_groupnorm_bwd: null pointer");
+    TAVK_CHECK(C % 64 == 0 && R >= T && T > 0 && B > 0, 1, "tavk_groupnorm_bwd: C %% 64 == 0 required (C=%d)", C);
+    TAVK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * 2 * C * sizeof(float), stream));
+    dim3 g1(C / 64, (T + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B), g2(C / 64, (R + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B);
+    groupnorm_bwd_stats_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
+                                                       reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, sums_ws, R, T, C);
+    groupnorm_bwd_apply_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
+                                                       reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, gamma, sums_ws,
+                                                       reinterpret_cast<__nv_bfloat16*>(du), R, T, C);
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_wave_windows(const float* wav, void* win, int B, int L, int R, int T, int k, int s, void* stream) {
+    TAVK_CHECK(wav && win, 1, "tavk_wave_windows: null pointer");
+    TAVK_CHECK(k >= 1 && k <= 16 && s >= 1 && B > 0 && R >= T, 1, "tavk_wave_windows: 1 <= k <= 16 (k=%d)", k);
+    const long long total = (long long)B * R * 16;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    wave_windows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        wav, reinterpret_cast<__nv_bfloat16*>(win), L, R, T, k, s, total);
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

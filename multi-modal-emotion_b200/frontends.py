@@ -65,8 +65,9 @@ class _ConvFeatureEncoderFn(torch.autograd.Function):
         pres = [torch.empty((B * R[l], C), dtype=torch.bfloat16, device=dev) for l in range(n)]
         mean = torch.empty((B, C), dtype=torch.float32, device=dev)
         rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        sums = torch.empty((B, 2, C), dtype=torch.float32, device=dev)
         L.call("tavk_groupnorm_gelu_fwd", u0.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), pres[0].data_ptr(),
-               acts[0].data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, R[0], T[0], C, float(eps))
+               acts[0].data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(), B, R[0], T[0], C, float(eps))
         for l in range(1, n):
             k, st = kernels[l], strides[l]
             wk = L.cast_bf16(weights[l].detach().permute(0, 2, 1).contiguous().view(C, k * C))
@@ -117,13 +118,20 @@ class _ConvFeatureEncoderFn(torch.autograd.Function):
             L.gemm(dpre, b2.view(st * C, d * C), nxt[lead_prev:].view(M, st * C), M=M, N=st * C, K=d * C, lda=C,
                    aux=pres[l - 1].view(M, st * C), epilogue=L.EPI_GELU_BWD)
             dpre = nxt
-        # layer 0: GroupNorm + conv over the waveform (dpre now holds dz0)
-        dgw, dgb = torch.zeros_like(gn_w), torch.zeros_like(gn_w)
-        dw0 = torch.zeros_like(weights[0])
-        L.call("tavk_groupnorm_conv0_bwd", dpre.data_ptr(), u0.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-               gn_w.data_ptr(), wav.data_ptr(), dgw.data_ptr(), dgb.data_ptr(), dw0.data_ptr(), None, B, Lp, R[0], T[0],
-               C, kernels[0], strides[0])
-        grads[0] = dw0
+        # layer 0 (dpre now holds dz0): GroupNorm backward in place -> du0; affine gradients from its per-sample sums;
+        # conv0 weight gradient = wgrad GEMM of du0 against the waveform's window matrix (C_in = 1: 16 bf16 per row)
+        k0, s0 = kernels[0], strides[0]
+        sums = torch.empty((B, 2, C), dtype=torch.float32, device=dev)
+        L.call("tavk_groupnorm_bwd", dpre.data_ptr(), u0.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gn_w.data_ptr(),
+               dpre.data_ptr(), sums.data_ptr(), B, R[0], T[0], C)
+        dgb, dgw = sums[:, 0].sum(dim=0), sums[:, 1].sum(dim=0)
+        win = torch.empty((B * R[0], 16), dtype=torch.bfloat16, device=dev)
+        L.call("tavk_wave_windows", wav.data_ptr(), win.data_ptr(), B, Lp, R[0], T[0], k0, s0)
+        dw0 = torch.zeros((C, 16), dtype=torch.float32, device=dev)
+        M0 = B * R[0]
+        L.gemm(dpre, win, dw0, M=C, N=16, K=M0, lda=C, ldb=16, a_mn=True, b_mn=True, accumulate=True,
+               k_splits=max(1, min(148 // ((C + 127) // 128), (M0 + 2047) // 2048)))
+        grads[0] = dw0[:, :k0].reshape(weights[0].shape)
         return (None, dgw, dgb, None, None, None, *grads)
 
 
