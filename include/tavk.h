@@ -142,10 +142,12 @@ int tavk_attn_bwd(const tavk_attn_bwd_args* args, void* stream);
 int tavk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
                        float* rstd, int M, int H, float eps, void* stream);
 /* dx = (dx_resid or 0) + LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy (atomic accumulation into f32 [H]).
- * dy is f32 [M,H]; dx_f32 and/or dx_bf16 (a bf16 copy for the next dgrad/wgrad GEMM) may be NULL. */
+ * dy is f32 [M,H]; dx_f32 and/or dx_bf16 (a bf16 copy for the next dgrad/wgrad GEMM) may be NULL.
+ * dx_colsum (f32 [H] or NULL): += column sums of dx — the bias gradient of the Linear whose output x is, so no
+ * separate pass over dx is needed for it. */
 int tavk_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                       const float* dx_resid, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int M, int H,
-                       void* stream);
+                       const float* dx_resid, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                       float* dx_colsum, int M, int H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Memory-bound helpers of the path. */

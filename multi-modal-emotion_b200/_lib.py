@@ -74,7 +74,7 @@ SIGNATURES = {
     "tavk_attn_fwd": [C.POINTER(AttnArgs), _P],
     "tavk_attn_bwd": [C.POINTER(AttnBwdArgs), _P],
     "tavk_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
-    "tavk_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "tavk_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_embed_add_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "tavk_embed_add_bwd": [_P, _P, _P, _I, _I, _I, _P],
     "tavk_mean_pool_fwd": [_P, _P, _I, _I, _I, _P],
@@ -222,13 +222,15 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False):
     return yb, yf, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, resid=None, want_f32=True, want_bf16=False):
-    """Returns (dx_f32|None, dx_bf16|None); dgamma/dbeta are accumulated into (f32 [H])."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, resid=None, want_f32=True, want_bf16=False,
+                  dx_colsum=None):
+    """Returns (dx_f32|None, dx_bf16|None); dgamma/dbeta (and dx_colsum, the column sums of dx) are accumulated into
+    f32 [H] buffers."""
     M, H = x.shape
     dxf = torch.empty((M, H), dtype=torch.float32, device=x.device) if want_f32 else None
     dxb = torch.empty((M, H), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     call("tavk_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-         _ptr(resid), _ptr(dxf), _ptr(dxb), _ptr(dgamma), _ptr(dbeta), M, H)
+         _ptr(resid), _ptr(dxf), _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum), M, H)
     return dxf, dxb
 
 

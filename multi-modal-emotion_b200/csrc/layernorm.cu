@@ -73,7 +73,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const float* __restrict__ dx_resid, float* __restrict__ dx_f32,
                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int M) {
+                     float* __restrict__ dx_colsum, int M) {
     constexpr int H = VEC * 128;
     extern __shared__ float red[];  // [warps][H]
     const int lane = threadIdx.x & 31;
@@ -82,11 +82,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     float4 g4[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g4[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-    float4 dg[VEC], db[VEC];
+    float4 dg[VEC], db[VEC], dc[VEC];   // dc: column sums of dx (the bias gradient of the Linear that produced x)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int row = blockIdx.x * warps_per_block + warp; row < M; row += gridDim.x * warps_per_block) {
         const float mu = mean[row], rs = rstd[row];
@@ -121,6 +122,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                 const float4 r = reinterpret_cast<const float4*>(dx_resid + (size_t)row * H)[lane + 32 * i];
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
+            dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w;
             if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * H)[lane + 32 * i] = o;
             if (dx_bf16) {
                 uint2 p;
@@ -130,15 +132,15 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             }
         }
     }
-    // block reduction of the parameter gradients, dgamma then dbeta through the same smem buffer
+    // block reduction of the parameter gradients, dgamma, dbeta, then the dx column sums through the same smem buffer
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        float* out = pass == 0 ? dgamma : dbeta;
+    for (int pass = 0; pass < 3; ++pass) {
+        float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
         if (out == nullptr) continue;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < VEC; ++i)
-            reinterpret_cast<float4*>(red + warp * H)[lane + 32 * i] = pass == 0 ? dg[i] : db[i];
+            reinterpret_cast<float4*>(red + warp * H)[lane + 32 * i] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dc[i]);
         __syncthreads();
         for (int c = threadIdx.x; c < H; c += blockDim.x) {
             float s = 0.f;
@@ -177,7 +179,7 @@ extern "C" int tavk_layernorm_fwd(const float* x, const float* gamma, const floa
 
 extern "C" int tavk_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* dx_resid, float* dx_f32, void* dx_bf16,
-                                  float* dgamma, float* dbeta, int M, int H, void* stream_) {
+                                  float* dgamma, float* dbeta, float* dx_colsum, int M, int H, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     TAVK_CHECK(dy && x && mean && rstd && gamma, 1, "tavk_layernorm_bwd: null pointer");
     TAVK_CHECK(M >= 0 && H > 0, 1, "tavk_layernorm_bwd: bad shape M=%d H=%d", M, H);
@@ -193,7 +195,7 @@ extern "C" int tavk_layernorm_bwd(const float* dy, const float* x, const float* 
 #define LN_BWD(V)                                                                                                  \
     case V:                                                                                                        \
         layernorm_bwd_kernel<V><<<grid, warps * 32, smem, stream>>>(dy, x, mean, rstd, gamma, dx_resid, dx_f32, db16, \
-                                                                   dgamma, dbeta, M);                              \
+                                                                   dgamma, dbeta, dx_colsum, M);                   \
         break;
     switch (H / 128) {
         LN_BWD(1) LN_BWD(2) LN_BWD(3) LN_BWD(4) LN_BWD(5) LN_BWD(6) LN_BWD(7) LN_BWD(8)

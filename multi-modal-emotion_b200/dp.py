@@ -61,10 +61,20 @@ class GradBuckets:
 
     def start_backward(self):
         """Arm the buckets for one backward pass."""
+        from . import engine
+
         self.pending = [n for (_, _, n) in self.buckets]
         self.works = []
         self.enabled = True
         self.launched = 0
+        # parameters whose gradient the layer engine accumulates straight into the flat buffer never reach autograd's
+        # AccumulateGrad (and so never fire the hooks above): the engine reports them layer by layer instead
+        engine.grad_written_hook = self._written
+
+    def _written(self, params):
+        for p in params:
+            if id(p) in self.param_bucket:
+                self._hook(p)
 
     def _launch(self, b):
         s, e, _ = self.buckets[b]
@@ -87,6 +97,9 @@ class GradBuckets:
 
     def finish(self):
         """Reduce whatever did not fire from a hook (parameters without a gradient this step) and wait."""
+        from . import engine
+
+        engine.grad_written_hook = None
         if self.enabled:
             for b, n in enumerate(self.pending):
                 if n > 0:

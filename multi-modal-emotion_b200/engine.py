@@ -85,12 +85,33 @@ def _wgrad_splits(rows_out, cols_out, k_tokens):
     return s
 
 
-def _wgrad(dy_bf, x_bf, rows_out, cols_out, tokens):
-    """dW[rows_out, cols_out] = dY^T · X over `tokens` rows; both operands MN-major views of row-major activations."""
-    out = torch.zeros((rows_out, cols_out), dtype=torch.float32, device=dy_bf.device)
+def _wgrad(dy_bf, x_bf, rows_out, cols_out, tokens, out=None, lda=None):
+    """dW[rows_out, cols_out] (+)= dY^T · X over `tokens` rows; both operands MN-major views of row-major activations.
+    ``out``: an existing fp32 gradient buffer to accumulate into (the parameter's .grad slice); else a new tensor."""
+    if out is None:
+        out = torch.zeros((rows_out, cols_out), dtype=torch.float32, device=dy_bf.device)
     ks = _wgrad_splits(rows_out, cols_out, tokens)
-    L.gemm(dy_bf, x_bf, out, M=rows_out, N=cols_out, K=tokens, a_mn=True, b_mn=True, accumulate=True, k_splits=ks)
+    L.gemm(dy_bf, x_bf, out, M=rows_out, N=cols_out, K=tokens, a_mn=True, b_mn=True, accumulate=True, k_splits=ks, lda=lda)
     return out
+
+
+# Gradient sink: when a parameter already owns a contiguous fp32 ``.grad`` (optim.FlatParams points every .grad at a
+# slice of one flat buffer, zeroed by the fused AdamW kernel), the stack's backward accumulates straight into it — the
+# wgrad GEMMs' red.global.add epilogue, the LayerNorm / column-sum atomics — and returns None for that input, instead
+# of materialising a temporary and letting autograd launch one add_ per parameter.  Because autograd's
+# post-accumulate-grad hooks do not fire for such parameters, ``grad_written_hook(params)`` is called after each
+# layer's kernels are enqueued (dp.GradBuckets uses it to launch bucket all-reduces during backward).
+grad_sink_enabled = True
+grad_written_hook = None
+
+
+def _sink(t):
+    if not grad_sink_enabled or t is None:
+        return None
+    g = t.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != t.shape or not g.is_cuda:
+        return None
+    return g
 
 
 def _f32(shape, dev):
@@ -187,72 +208,104 @@ def _attention_bwd(spec, sv, do, B, S, mask2d, dc):
     return dqkv
 
 
-def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf):
-    """Returns (dx_f32, dx_bf16|None, grads list aligned with PARAM_SLOTS)."""
+class _GradOut:
+    """Per-layer gradient targets: the parameter's own .grad (sink) or a fresh zero buffer returned to autograd."""
+
+    def __init__(self, p, dev):
+        self.d = dict(zip(PARAM_SLOTS, p))
+        self.sink = {n: _sink(t) for n, t in self.d.items()}
+        self.tmp = {}
+        self.dev = dev
+
+    def target(self, name):
+        """fp32 buffer to ACCUMULATE the gradient of slot `name` into (None when the layer has no such parameter)."""
+        t = self.d[name]
+        if t is None:
+            return None
+        if self.sink[name] is not None:
+            return self.sink[name]
+        if name not in self.tmp:
+            self.tmp[name] = torch.zeros(t.shape, dtype=torch.float32, device=self.dev)
+        return self.tmp[name]
+
+    def results(self):
+        return [self.tmp.get(n) if (self.d[n] is not None and self.sink[n] is None) else None for n in PARAM_SLOTS]
+
+    def written(self):
+        return [self.d[n] for n in PARAM_SLOTS if self.d[n] is not None and self.sink[n] is not None]
+
+
+def _qkv_grads(go, dqkv, x_bf, H, M):
+    """dW_q/k/v and db_q/k/v from the packed dqkv [M, 3H]: one [3H, H] wgrad GEMM when the three weight-gradient
+    targets are adjacent in memory (flat-buffer order q, k, v), else one GEMM per matrix."""
+    tq, tk, tv = go.target("wq"), go.target("wk"), go.target("wv")
+    step = H * H * 4
+    if tk.data_ptr() - tq.data_ptr() == step and tv.data_ptr() - tk.data_ptr() == step:
+        _wgrad(dqkv, x_bf, 3 * H, H, M, out=tq)     # tq is the base of the adjacent [3H, H] block
+    else:
+        for i, t in enumerate((tq, tk, tv)):
+            _wgrad(dqkv[:, i * H:(i + 1) * H], x_bf, H, H, M, out=t, lda=3 * H)
+    for i, n in enumerate(("bq", "bk", "bv")):
+        t = go.target(n)
+        if t is not None:
+            L.colsum(dqkv[:, i * H:(i + 1) * H], t, M=M, N=H, ld=3 * H, accumulate=True)
+
+
+def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=False, dx_colsum=None):
+    """Returns (dx_f32, dx_bf16|None, grads list aligned with PARAM_SLOTS — None where the gradient went to the sink —,
+    parameters whose .grad was written directly).
+    ``b2_done``: the column sums of dy (this layer's b2 gradient) were already accumulated by the layer above's
+    LayerNorm backward; ``dx_colsum``: where to accumulate the column sums of dx (the b2 gradient of the layer below)."""
     H, I = spec.hidden, spec.inter
     M = B * S
     dev = dy.device
     d = dict(zip(PARAM_SLOTS, p))
-    g = dict.fromkeys(PARAM_SLOTS)
-    zeros = lambda n: torch.zeros((n,), dtype=torch.float32, device=dev)  # noqa: E731
+    go = _GradOut(p, dev)
     if spec.pre_ln:
         if dy_bf is None:
             dy_bf = L.cast_bf16(dy)
         # FFN down
-        g["b2"] = _f32((H,), dev)
-        L.colsum(dy, g["b2"], M=M, N=H)
-        g["w2"] = _wgrad(dy_bf, sv.act, H, I, M)
+        if not b2_done and d["b2"] is not None:
+            L.colsum(dy, go.target("b2"), M=M, N=H, accumulate=True)
+        _wgrad(dy_bf, sv.act, H, I, M, out=go.target("w2"))
         dpre = _bf16((M, I), dev)
-        g["b1"] = zeros(I)   # column sums of dpre, accumulated by the GEMM epilogue
-        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=g["b1"])
+        # the GELU' dgrad GEMM also accumulates the column sums of dpre (= b1 gradient) in its epilogue
+        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=go.target("b1"))
         # FFN up
-        g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
+        _wgrad(dpre, sv.h2, I, H, M, out=go.target("w1"))
         dh2 = _f32((M, H), dev)
         L.gemm(dpre, sh.w1, dh2, M=M, N=H, K=I, b_mn=True)
-        g["ln2_w"], g["ln2_b"] = zeros(H), zeros(H)
-        dx1, dx1_bf = L.layernorm_bwd(dh2, sv.x1, sv.mean2, sv.rstd2, d["ln2_w"], g["ln2_w"], g["ln2_b"], resid=dy,
-                                      want_f32=True, want_bf16=True)
-        # attention out-projection
-        g["bo"] = _f32((H,), dev)
-        L.colsum(dx1, g["bo"], M=M, N=H)
-        g["wo"] = _wgrad(dx1_bf, sv.o, H, H, M)
+        # LayerNorm backward also emits the column sums of dx1 (= out-projection bias gradient)
+        dx1, dx1_bf = L.layernorm_bwd(dh2, sv.x1, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
+                                      resid=dy, want_f32=True, want_bf16=True, dx_colsum=go.target("bo"))
+        wo_t = _wgrad(dx1_bf, sv.o, H, H, M, out=go.target("wo"))
         dc = None
         if spec.mask_mode == "rank1":
             drb = _f32((B, H), dev)
             L.masked_colsum(dx1, None, drb, B=B, S=S, N=H, ld=H)
             dc = _f32((B, H), dev)
             L.call("tavk_small_linear_bwd_x", drb.data_ptr(), d["wo"].data_ptr(), dc.data_ptr(), B, H, H, 0)
-            L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), g["wo"].data_ptr(), None, B, H, H)
+            L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), wo_t.data_ptr(), None, B, H, H)
         do = _bf16((M, H), dev)
         L.gemm(dx1_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
         dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, dc)
-        dbqkv = _f32((3 * H,), dev)
-        L.colsum(dqkv, dbqkv, M=M, N=3 * H)
-        dwqkv = _wgrad(dqkv, sv.h1, 3 * H, H, M)
+        _qkv_grads(go, dqkv, sv.h1, H, M)
         dh1 = _f32((M, H), dev)
         L.gemm(dqkv, sh.wqkv, dh1, M=M, N=H, K=3 * H, b_mn=True)
-        g["ln1_w"], g["ln1_b"] = zeros(H), zeros(H)
-        dx, dx_bf = L.layernorm_bwd(dh1, sv.x, sv.mean1, sv.rstd1, d["ln1_w"], g["ln1_w"], g["ln1_b"], resid=dx1,
-                                    want_f32=True, want_bf16=need_dx_bf)
+        dx, dx_bf = L.layernorm_bwd(dh1, sv.x, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
+                                    resid=dx1, want_f32=True, want_bf16=need_dx_bf, dx_colsum=dx_colsum)
     else:
-        g["ln2_w"], g["ln2_b"] = zeros(H), zeros(H)
-        df, df_bf = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], g["ln2_w"], g["ln2_b"], want_f32=True,
-                                    want_bf16=True)
-        g["b2"] = _f32((H,), dev)
-        L.colsum(df, g["b2"], M=M, N=H)
-        g["w2"] = _wgrad(df_bf, sv.act, H, I, M)
+        df, df_bf = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
+                                    want_f32=True, want_bf16=True, dx_colsum=go.target("b2"))
+        _wgrad(df_bf, sv.act, H, I, M, out=go.target("w2"))
         dpre = _bf16((M, I), dev)
-        g["b1"] = zeros(I)   # column sums of dpre, accumulated by the GEMM epilogue
-        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=g["b1"])
-        g["w1"] = _wgrad(dpre, sv.h2, I, H, M)
+        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=go.target("b1"))
+        _wgrad(dpre, sv.h2, I, H, M, out=go.target("w1"))
         dyl = _f32((M, H), dev)
         L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)
-        g["ln1_w"], g["ln1_b"] = zeros(H), zeros(H)
-        da, da_bf = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], g["ln1_w"], g["ln1_b"], want_f32=True,
-                                    want_bf16=True)
-        g["bo"] = _f32((H,), dev)
-        L.colsum(da, g["bo"], M=M, N=H)
-        g["wo"] = _wgrad(da_bf, sv.o_used, H, H, M)
+        da, da_bf = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
+                                    want_f32=True, want_bf16=True, dx_colsum=go.target("bo"))
+        _wgrad(da_bf, sv.o_used, H, H, M, out=go.target("wo"))
         do = _bf16((M, H), dev)
         L.gemm(da_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
         if spec.scrambled_concat:
@@ -260,17 +313,11 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf):
             L.call("tavk_permute_bshd_bhds", do.data_ptr(), do2.data_ptr(), B, S, spec.heads, H // spec.heads, 1)
             do = do2
         dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, None)
-        dbqkv = _f32((3 * H,), dev)
-        L.colsum(dqkv, dbqkv, M=M, N=3 * H)
-        dwqkv = _wgrad(dqkv, sv.x_bf, 3 * H, H, M)
+        _qkv_grads(go, dqkv, sv.x_bf, H, M)
         dx = _f32((M, H), dev)
         L.gemm(dqkv, sh.wqkv, dx, M=M, N=H, K=3 * H, b_mn=True, resid=da)
         dx_bf = None
-    for i, (wn, bn) in enumerate((("wq", "bq"), ("wk", "bk"), ("wv", "bv"))):
-        g[wn] = dwqkv[i * H:(i + 1) * H]
-        if d[bn] is not None:
-            g[bn] = dbqkv[i * H:(i + 1) * H]
-    return dx, dx_bf, [g[n] if d[n] is not None else None for n in PARAM_SLOTS]
+    return dx, dx_bf, go.results(), go.written()
 
 
 class EncoderStackFn(torch.autograd.Function):
@@ -305,12 +352,29 @@ class EncoderStackFn(torch.autograd.Function):
             dy = dy.float()
         dy_bf = None
         grads = [None] * len(ctx.params)
+        b2_done = False
+        i_b2 = PARAM_SLOTS.index("b2")
         for li in range(n_layers - 1, -1, -1):
             p = ctx.params[li * N_SLOTS:(li + 1) * N_SLOTS]
-            dy, dy_bf, g = _layer_bwd(spec, p, ctx.shadows[li], ctx.saved[li], dy, dy_bf, B, S, ctx.mask2d,
-                                      need_dx_bf=(li > 0 and spec.pre_ln))
+            # pre-LN stacks: this layer's last LayerNorm backward also accumulates the column sums of its dx, which
+            # are the b2 gradient of the layer below (into that parameter's .grad, or a buffer handed back to autograd)
+            below_b2 = ctx.params[(li - 1) * N_SLOTS + i_b2] if (li > 0 and spec.pre_ln) else None
+            cs_t, cs_tmp = None, None
+            if below_b2 is not None:
+                cs_t = _sink(below_b2)
+                if cs_t is None:
+                    cs_t = cs_tmp = torch.zeros(below_b2.shape, dtype=torch.float32, device=dy.device)
+            dy, dy_bf, g, written = _layer_bwd(spec, p, ctx.shadows[li], ctx.saved[li], dy, dy_bf, B, S, ctx.mask2d,
+                                               need_dx_bf=(li > 0 and spec.pre_ln), b2_done=b2_done, dx_colsum=cs_t)
             ctx.saved[li] = None  # free activations as we go
-            grads[li * N_SLOTS:(li + 1) * N_SLOTS] = g
+            for k, gk in enumerate(g):
+                if gk is not None:
+                    grads[li * N_SLOTS + k] = gk if grads[li * N_SLOTS + k] is None else grads[li * N_SLOTS + k] + gk
+            if cs_tmp is not None:
+                grads[(li - 1) * N_SLOTS + i_b2] = cs_tmp
+            b2_done = below_b2 is not None
+            if grad_written_hook is not None and written:
+                grad_written_hook(written)
         return (None, None, dy.view(B, S, H), None, *grads)
 
 

@@ -174,8 +174,11 @@ def test_layernorm_fwd_bwd(L, M, H, eps, big):
     ref.backward(dy.double())
     dgamma = torch.zeros(H, device="cuda")
     dbeta = torch.zeros(H, device="cuda")
-    dxf, dxb = L.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=resid, want_f32=True, want_bf16=True)
+    dcs = torch.full((H,), 1.5, device="cuda")
+    dxf, dxb = L.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=resid, want_f32=True, want_bf16=True,
+                               dx_colsum=dcs)
     ref_dx = xd.grad + resid.double()
+    assert rel_l2(dcs, 1.5 + ref_dx.sum(dim=0)) < (1e-5 if not big else 1e-3)   # fused bias-gradient column sums
     assert rel_l2(dxf, ref_dx) < (1e-5 if not big else 1e-3)
     assert rel_l2(dxb, ref_dx) < 5e-3
     assert rel_l2(dgamma, gd.grad) < (1e-5 if not big else 1e-3)
