@@ -18,6 +18,8 @@
 //               when it grows by more than 8 in the log2 domain, so the common path never touches O.
 // Epilogue: O / l -> bf16 rows, lse = (m + log2 l) ln2.
 #include "../../include/tavk.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tavk {
@@ -46,6 +48,14 @@ TAVK_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
 }
 TAVK_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 32 fp32 accumulator columns of this thread's row -> bf16 -> 64 contiguous bytes in global
+TAVK_DEVINL void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+}
 struct AttnTcDev {
     __nv_bfloat16* o;
     long long ld_o;
@@ -233,6 +243,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         lp[half * 128 + row] = l;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         l = lp[row] + lp[128 + row];
+        // pv_done completes one phase per PV(j); a parity wait only tells "odd or even number of completions", and this
+        // warp is only known to be past PV(n-3) (the P-buffer hand-off): wait for PV(n-2) first, then for PV(n-1)
+        if (n_tiles >= 2) mbar_wait(pv_done, (n_tiles - 2) & 1);
         mbar_wait(pv_done, (n_tiles - 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;
@@ -258,6 +271,223 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (warp_idx == 1) {
         tc_fence_after();
         tmem_dealloc<kTcTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// Forward, v3: the same pipeline cut to HALF the footprint so that TWO CTAs share an SM (192 threads, 97 KB of shared
+// memory, 256 TMEM columns each).  With head_dim 64 the kernel is bound by the softmax (16 exp/clk/SM against 8192
+// tensor FLOP/clk/SM: a 128x128 score tile costs 1024 MUFU cycles but only 512 tensor cycles), so what matters is that
+// the MUFU pipe never idles: two independent CTAs per SM are in different phases (one in row-max / packing / barrier
+// hand-offs while the other streams ex2), which the single-CTA version above could not do with 2 warps per scheduler.
+//   KV tile = 64 keys; one softmax THREAD per query row (4 warps): no cross-warp max/sum exchange, no named barriers.
+//   S double-buffered in TMEM (2 x 64 columns) + O (64 columns); P double-buffered in smem (2 x 16 KB).
+// =====================================================================================================
+constexpr int kF3KV = 64;
+constexpr int kF3Stages = 3;
+constexpr int kF3KTile = kF3KV * kTcD * 2;            // 8 KB (K or V tile)
+constexpr int kF3PBytes = kTcQ * kF3KV * 2;           // 16 KB
+constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 2 * kF3PBytes + 1024 + 256;   // 97.25 KB + slack
+constexpr int kF3Threads = 6 * 32;
+constexpr uint32_t kF3TmemCols = 256;
+
+__global__ void __launch_bounds__(kF3Threads, 2)
+attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + kTcTile;
+    uint8_t* sV = sK + kF3Stages * kF3KTile;
+    uint8_t* sP = sV + kF3Stages * kF3KTile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kF3PBytes);
+    uint64_t* q_full = bars;               // 1
+    uint64_t* kv_full = bars + 1;          // kF3Stages
+    uint64_t* kv_empty = kv_full + kF3Stages;
+    uint64_t* s_full = kv_empty + kF3Stages;  // 2
+    uint64_t* p_full = s_full + 2;            // 2
+    uint64_t* p_empty = p_full + 2;           // 2
+    uint64_t* pv_done = p_empty + 2;          // 1
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
+    const int q0 = blockIdx.x * kTcQ, h = blockIdx.y, b = blockIdx.z;
+    const int n_tiles = (p.S + kF3KV - 1) / kF3KV;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < kF3Stages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+        mbar_init(pv_done, 1);
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<kF3TmemCols>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    const uint32_t tmem_o = tmem_base + 2 * kF3KV;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kTcTile);
+            tma_load_3d(sQ, &tmap_q, q_full, h * kTcD, q0, b);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j % kF3Stages;
+                mbar_wait(&kv_empty[st], ((j / kF3Stages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * kF3KTile);
+                tma_load_3d(sK + st * kF3KTile, &tmap_k, &kv_full[st], h * kTcD, j * kF3KV, b);
+                tma_load_3d(sV + st * kF3KTile, &tmap_v, &kv_full[st], h * kTcD, j * kF3KV, b);
+            }
+        }
+    } else if (warp_idx == 1) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(kTcQ, kF3KV, false, false);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(kTcQ, kTcD, false, true);
+        const uint64_t dq0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+        const uint64_t dk0 = umma_smem_desc(smem_u32(sK), 16, 1024);
+        const uint64_t dv0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
+        const uint64_t dp0 = umma_smem_desc(smem_u32(sP), 16, 1024);
+        auto issue_qk = [&](int j) {
+            const int st = j % kF3Stages;
+            mbar_wait(&kv_full[st], (j / kF3Stages) & 1);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t dk = dk0 + (uint64_t)(st * (kF3KTile >> 4));
+                const uint32_t tmem_s = tmem_base + (j & 1) * kF3KV;
+#pragma unroll
+                for (int k = 0; k < kTcD / 16; ++k) umma_bf16(tmem_s, dq0 + 2 * k, dk + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[j & 1]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            if (j + 1 < n_tiles) issue_qk(j + 1);
+            mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            if (leader) {
+                const int st = j % kF3Stages;
+                const uint64_t dp = dp0 + (uint64_t)((j & 1) * (kF3PBytes >> 4));
+                const uint64_t dv = dv0 + (uint64_t)(st * (kF3KTile >> 4));
+#pragma unroll
+                for (int k = 0; k < kF3KV / 16; ++k)
+                    umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv,
+                              (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[st]);
+                umma_commit(&p_empty[j & 1]);
+                umma_commit(pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax / epilogue: one thread per query row, all 64 key columns of the tile ============
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sr[64];
+            const uint32_t ts = tmem_base + lane_sel + (uint32_t)((j & 1) * kF3KV);
+            tmem_ld_32x32(ts + 0, reinterpret_cast<uint32_t(&)[32]>(sr[0]));
+            tmem_ld_32x32(ts + 32, reinterpret_cast<uint32_t(&)[32]>(sr[32]));
+            tmem_ld_wait();
+            const int valid = p.S - j * kF3KV;   // key columns of this tile that exist
+            float mx = -INFINITY;
+            if (valid >= 64) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) {
+                    if (c >= valid) sr[c] = 0xff800000u;  // -inf
+                    mx = fmaxf(mx, __uint_as_float(sr[c]));
+                }
+            }
+            mx *= p.scale_log2;
+            float factor = 1.0f;
+            const bool grow = mx > m_used + kRescaleThreshold;   // always true on the first tile (m_used = -inf)
+            if (grow) {
+                factor = ex2_approx(m_used - mx);                 // 0 on the first tile
+                l *= factor;
+                m_used = mx;
+            }
+            float sum = 0.f;
+            const float neg_m = -m_used;
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
+                sum += p0 + p1;
+                sr[c >> 1] = pack_bf16x2(p0, p1);
+            }
+            l += sum;
+            // P[j&1] must no longer be read by PV(j-2)
+            if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
+            const uint32_t pbase = smem_u32(sP + (j & 1) * kF3PBytes) + row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
+                             "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
+                             : "memory");
+            }
+            // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t orow[32];
+                    const uint32_t to = tmem_o + lane_sel + hh * 32;
+                    tmem_ld_32x32(to, orow);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
+                    tmem_st_32x32(to, orow);
+                }
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();   // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[j & 1]);
+        }
+        // ---- epilogue: normalise and store this thread's 64-column output row (128 contiguous bytes)
+        // pv_done completes one phase per PV(j); a parity wait only tells "odd or even number of completions", and this
+        // warp is only known to be past PV(n-3) (the P-buffer hand-off): wait for PV(n-2) first, then for PV(n-1)
+        if (n_tiles >= 2) mbar_wait(pv_done, (n_tiles - 2) & 1);
+        mbar_wait(pv_done, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const int qrow = q0 + row;
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t orow[32];
+            tmem_ld_32x32(tmem_o + lane_sel + hh * 32, orow);
+            tmem_ld_wait();
+            if (qrow < p.S) {
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(orow[c]) * inv;
+                store_row32_bf16(p.o + ((long long)b * p.S + qrow) * p.ld_o + h * kTcD + hh * 32, v);
+            }
+        }
+        if (qrow < p.S && p.lse)
+            p.lse[((long long)b * p.nh + h) * p.S + qrow] = l > 0.f ? (m_used + log2f(l)) * kTcLn2 : -INFINITY;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<kF3TmemCols>(tmem_base);
     }
 }
 
@@ -288,14 +518,6 @@ struct AttnTcBwdDev {
     float scale, scale_log2;
 };
 
-// 32 fp32 accumulator columns of this thread's row -> bf16 -> 64 contiguous bytes in global
-TAVK_DEVINL void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-}
 // 32 packed-pair registers (= 64 bf16... here 16 regs = 32 bf16) -> this row's 4 swizzled 16-byte chunks
 TAVK_DEVINL void st_row_chunks(uint32_t tile_base, int row, int half, const uint32_t (&pk)[16]) {
 #pragma unroll
@@ -686,12 +908,23 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale_log2 = a->scale * kTcLog2e;
     static bool attr_done = false;
+    static int use_v2 = 0;
     if (!attr_done) {
         TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+        const char* e = getenv("TAVK_ATTN_FWD_V2");    // A/B switch for profiling: the one-CTA-per-SM 128-key kernel
+        use_v2 = (e != nullptr && e[0] == '1');
         attr_done = true;
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
-    attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(tq, tk, tv, d);
+    if (use_v2) {
+        attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(tq, tk, tv, d);
+    } else {
+        CUtensorMap tk64, tv64;
+        if ((rc = make_tmap_bsd(&tk64, a->k, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
+        if ((rc = make_tmap_bsd(&tv64, a->v, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
+        attn_fwd_tc64_kernel<<<grid, kF3Threads, kF3Smem, stream>>>(tq, tk64, tv64, d);
+    }
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

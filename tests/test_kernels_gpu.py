@@ -151,6 +151,35 @@ def test_attention_fwd_bwd(L, B, S, nh, use_bias):
     assert rel_l2(dqkv[..., 2 * H:], unpack(vf.grad) + rowscale[:, :, None] * rank1[:, None, :]) < 1.5e-2
 
 
+@pytest.mark.parametrize("B,S", [(16, 1464), (16, 323)])
+def test_attention_full_size_deterministic(L, B, S):
+    """BASELINE configs[1] shapes (VideoMAE S=1464, fusion S=323; 192 (b,h) pairs -> every SM holds two CTAs):
+    the tensor-core attention has no atomics, so repeated launches must agree bit for bit, forward and backward."""
+    nh, H = 12, 768
+    g = gen(11)
+    qkv = (torch.randn(B, S, 3 * H, generator=g) * 0.7).cuda().bfloat16()
+    do = torch.randn(B, S, H, generator=g).cuda().bfloat16()
+    q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+    outs = []
+    for _ in range(4):
+        o = torch.full((B, S, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(B, nh, S, device="cuda")
+        L.attn_fwd(q, k, v, o, lse, B=B, S=S, nh=nh, ld_qkv=3 * H, ld_o=H)
+        dqkv = torch.full((B, S, 3 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
+        delta = torch.empty(B, nh, S, device="cuda")
+        L.attn_bwd(q, k, v, o, do, lse, delta, dqkv[..., :H], dqkv[..., H:2 * H], dqkv[..., 2 * H:], B=B, S=S, nh=nh,
+                   ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H)
+        outs.append((o, lse, dqkv))
+    for o, lse, dqkv in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(lse, outs[0][1]) and torch.equal(dqkv, outs[0][2])
+    # one (batch, head) slice against fp32 torch
+    b, h = B - 1, nh - 1
+    sl = slice(h * 64, (h + 1) * 64)
+    ref = torch.softmax((q[b, :, sl].float() @ k[b, :, sl].float().t()) * 0.125, dim=-1) @ v[b, :, sl].float()
+    assert rel_l2(outs[0][0][b, :, sl], ref) < 6e-3
+    assert torch.isfinite(outs[0][2].float()).all()
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("M,H,eps", [(646, 768, 1e-12), (5168, 768, 1e-5), (37, 1024, 1e-5), (2, 768, 1e-5)])
 @pytest.mark.parametrize("big", [False, True])
