@@ -861,6 +861,379 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
 }
 
+// =====================================================================================================
+// Backward, v3: the same two kernels cut down so that TWO CTAs share an SM (192 threads, <= 98 KB shared memory,
+// 256 TMEM columns each), for the reason given at the v3 forward: the elementwise stage (ex2, dS) sets the pace and a
+// single CTA's 8 lock-stepped warps leave both the MUFU and the tensor pipe idle in turns.  One elementwise THREAD
+// per tile row handles the step's 64 columns as two 32-column halves; S/dP (TMEM) and P/dS (smem) are single
+// buffers — the overlap now comes from the co-resident CTA — and the Q/dO (K/V) ring has two stages.
+//   s_free: the elementwise warps have copied S/dP of the step out of TMEM -> the issuer may overwrite them.
+// =====================================================================================================
+constexpr int kB3Stages = 2;
+constexpr int kB3Threads = 6 * 32;
+constexpr int kDkv3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + 2 * kBwPBytes + kB3Stages * 128 * 4 + 1024 + 256;
+constexpr int kDq3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + kBwPBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kB3Threads, 2)
+attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                        const AttnTcBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + kTcTile;
+    uint8_t* sQ = sV + kTcTile;                       // ring: [stage] Q_i
+    uint8_t* sDO = sQ + kB3Stages * kBwSmall;         // ring: [stage] dO_i
+    uint8_t* sP = sDO + kB3Stages * kBwSmall;         // P^T
+    uint8_t* sDS = sP + kBwPBytes;                    // dS^T
+    float* s_stats = reinterpret_cast<float*>(sDS + kBwPBytes);   // ring: [stage][64 lse*log2e | 64 delta]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + kB3Stages * 128);
+    uint64_t* kv_full = bars;
+    uint64_t* qdo_full = bars + 1;
+    uint64_t* qdo_empty = qdo_full + kB3Stages;
+    uint64_t* st_full = qdo_empty + kB3Stages;
+    uint64_t* st_free = st_full + 1;
+    uint64_t* pds_full = st_free + 1;
+    uint64_t* pds_empty = pds_full + 1;
+    uint64_t* done = pds_empty + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < kB3Stages; ++i) { mbar_init(&qdo_full[i], 2); mbar_init(&qdo_empty[i], 1); }  // TMA + stats
+        mbar_init(st_full, 1); mbar_init(st_free, 4); mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<256>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    const uint32_t tmem_dv = tmem_base + 128, tmem_dk = tmem_base + 192;
+
+    if (warp_idx == 0) {
+        // producer: lane 0 drives TMA; all lanes stage the per-query statistics of the step (lse*log2e, delta)
+        const long long stat_off = ((long long)b * p.nh + h) * p.S;
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * kTcTile);
+            tma_load_3d(sK, &tmap_k, kv_full, h * kTcD, k0, b);
+            tma_load_3d(sV, &tmap_v, kv_full, h * kTcD, k0, b);
+        }
+        for (int i = 0; i < n_steps; ++i) {
+            const int st = i % kB3Stages;
+            mbar_wait(&qdo_empty[st], ((i / kB3Stages) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
+                tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
+                tma_load_3d(sDO + st * kBwSmall, &tmap_do, &qdo_full[st], h * kTcD, i * kBwStep, b);
+            }
+#pragma unroll
+            for (int t = lane; t < kBwStep; t += 32) {
+                const int qi = i * kBwStep + t;
+                const bool ok = qi < p.S;
+                s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
+                s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qdo_full[st]);
+        }
+    } else if (warp_idx == 1) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S^T, dP^T
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dV, dK (B MN-major)
+        const uint64_t dK = umma_smem_desc(smem_u32(sK), 16, 1024), dV = umma_smem_desc(smem_u32(sV), 16, 1024);
+        const uint64_t dQk0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dDOk0 = umma_smem_desc(smem_u32(sDO), 16, 1024);
+        const uint64_t dQm0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dDOm0 = umma_smem_desc(smem_u32(sDO), 8192, 1024);
+        const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 16, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        mbar_wait(kv_full, 0);
+        tc_fence_after();
+        for (int i = 0; i <= n_steps; ++i) {
+            if (i < n_steps) {
+                const int st = i % kB3Stages;
+                mbar_wait(&qdo_full[st], (i / kB3Stages) & 1);
+                if (i >= 1) mbar_wait(st_free, (i - 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
+                    const uint32_t t_st = tmem_base, t_dp = tmem_base + 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+                    umma_commit(st_full);
+                }
+                __syncwarp();
+            }
+            if (i >= 1) {
+                const int kstep = i - 1, st = kstep % kB3Stages;
+                mbar_wait(pds_full, kstep & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dv, dP0 + 2 * k, dDOm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dk, dDS0 + 2 * k, dQm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&qdo_empty[st]);
+                    umma_commit(pds_empty);
+                }
+                __syncwarp();
+            }
+        }
+        if (leader) umma_commit(done);
+        __syncwarp();
+    } else {
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;                       // key row inside the tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        for (int i = 0; i < n_steps; ++i) {
+            const int stg = i % kB3Stages;
+            mbar_wait(&qdo_full[stg], (i / kB3Stages) & 1);        // the step's statistics are staged
+            mbar_wait(st_full, i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t s[32], dp[32];
+                tmem_ld_32x32(tmem_base + lane_sel + half * 32, s);
+                tmem_ld_32x32(tmem_base + lane_sel + 64 + half * 32, dp);
+                tmem_ld_wait();
+                if (half == 1) {   // S^T / dP^T of this step are in registers: the issuer may start step i+1
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(st_free);
+                }
+                // per-query statistics of the 32 columns: broadcast LDS.128 from the producer's staging ring
+                const uint32_t st_addr = smem_u32(s_stats + stg * 128 + half * 32);
+                uint32_t pk[16], dsk[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 l4 = ld_shared_v4(st_addr + c * 4), d4 = ld_shared_v4(st_addr + 256 + c * 4);
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -l4.x));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -l4.y));
+                    const float p2 = ex2_approx(fmaf(__uint_as_float(s[c + 2]), p.scale_log2, -l4.z));
+                    const float p3 = ex2_approx(fmaf(__uint_as_float(s[c + 3]), p.scale_log2, -l4.w));
+                    pk[c >> 1] = pack_bf16x2(p0, p1);
+                    pk[(c >> 1) + 1] = pack_bf16x2(p2, p3);
+                    dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - d4.x), p1 * (__uint_as_float(dp[c + 1]) - d4.y));
+                    dsk[(c >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[c + 2]) - d4.z), p3 * (__uint_as_float(dp[c + 3]) - d4.w));
+                }
+                if (half == 0 && i >= 1) mbar_wait(pds_empty, (i - 1) & 1);   // dV/dK MMAs of step i-1 have read P^T/dS^T
+                st_row_chunks(smem_u32(sP), row, half, pk);
+                st_row_chunks(smem_u32(sDS), row, half, dsk);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int key = k0 + row;
+        float w = 0.f;
+        const bool rank1 = p.dv_rowscale != nullptr && key < p.S;
+        if (rank1) w = p.dv_rowscale[(long long)b * p.S + key];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            float v[32];
+            const long long out_off = ((long long)b * p.S + key) * p.ld_dqkv + h * kTcD + half * 32;
+            tmem_ld_32x32(tmem_dk + lane_sel + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+            if (key < p.S) store_row32_bf16(p.dk + out_off, v);
+            // dV (+ rank-1 term of the post-softmax mask: dV[b,k,h,:] += m[b,k] * dc[b,h,:])
+            tmem_ld_32x32(tmem_dv + lane_sel + half * 32, r);
+            tmem_ld_wait();
+            const float* dc = rank1 ? p.dv_rank1 + ((long long)b * p.nh + h) * kTcD + half * 32 : nullptr;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) + (dc ? w * __ldg(dc + c) : 0.f);
+            if (key < p.S) store_row32_bf16(p.dv + out_off, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+__global__ void __launch_bounds__(kB3Threads, 2)
+attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                       const AttnTcBwdDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sDO = smem + kTcTile;
+    uint8_t* sK = sDO + kTcTile;                      // ring
+    uint8_t* sV = sK + kB3Stages * kBwSmall;          // ring
+    uint8_t* sDS = sV + kB3Stages * kBwSmall;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + kBwPBytes);
+    uint64_t* qdo_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + kB3Stages;
+    uint64_t* s_full = kv_empty + kB3Stages;
+    uint64_t* s_free = s_full + 1;
+    uint64_t* ds_full = s_free + 1;
+    uint64_t* ds_empty = ds_full + 1;
+    uint64_t* done = ds_empty + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
+
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+        mbar_init(qdo_full, 1);
+        for (int i = 0; i < kB3Stages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(ds_full, 4); mbar_init(ds_empty, 1);
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<256>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    const uint32_t tmem_dq = tmem_base + 128;
+
+    if (warp_idx == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qdo_full, 2 * kTcTile);
+            tma_load_3d(sQ, &tmap_q, qdo_full, h * kTcD, q0, b);
+            tma_load_3d(sDO, &tmap_do, qdo_full, h * kTcD, q0, b);
+            for (int j = 0; j < n_steps; ++j) {
+                const int st = j % kB3Stages;
+                mbar_wait(&kv_empty[st], ((j / kB3Stages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * kBwSmall);
+                tma_load_3d(sK + st * kBwSmall, &tmap_k, &kv_full[st], h * kTcD, j * kBwStep, b);
+                tma_load_3d(sV + st * kBwSmall, &tmap_v, &kv_full[st], h * kTcD, j * kBwStep, b);
+            }
+        }
+    } else if (warp_idx == 1) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S, dP
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
+        const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dDO = umma_smem_desc(smem_u32(sDO), 16, 1024);
+        const uint64_t dKk0 = umma_smem_desc(smem_u32(sK), 16, 1024), dVk0 = umma_smem_desc(smem_u32(sV), 16, 1024);
+        const uint64_t dKm0 = umma_smem_desc(smem_u32(sK), 8192, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        mbar_wait(qdo_full, 0);
+        tc_fence_after();
+        for (int j = 0; j <= n_steps; ++j) {
+            if (j < n_steps) {
+                const int st = j % kB3Stages;
+                mbar_wait(&kv_full[st], (j / kB3Stages) & 1);
+                if (j >= 1) mbar_wait(s_free, (j - 1) & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
+                    const uint32_t t_s = tmem_base, t_dp = tmem_base + 64;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_s, dQ + 2 * k, dKk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dDO + 2 * k, dVk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int kstep = j - 1, st = kstep % kB3Stages;
+                mbar_wait(ds_full, kstep & 1);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_dq, dDS0 + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&kv_empty[st]);
+                    umma_commit(ds_empty);
+                }
+                __syncwarp();
+            }
+        }
+        if (leader) umma_commit(done);
+        __syncwarp();
+    } else {
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;                       // query row inside the tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const int qrow = q0 + row;
+        const long long stat_off = ((long long)b * p.nh + h) * p.S;
+        const float lse2 = qrow < p.S ? p.lse[stat_off + qrow] * kTcLog2e : INFINITY;
+        const float dlt = qrow < p.S ? p.delta[stat_off + qrow] : 0.f;
+        for (int j = 0; j < n_steps; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t s[32], dp[32];
+                tmem_ld_32x32(tmem_base + lane_sel + half * 32, s);
+                tmem_ld_32x32(tmem_base + lane_sel + 64 + half * 32, dp);
+                tmem_ld_wait();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                }
+                const int valid = p.S - (j * kBwStep + half * 32);     // key columns of this slab that exist
+                uint32_t dsk[16];
+                if (valid >= 32) {                                     // uniform: only the last step has a ragged edge
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2));
+                        dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt), p1 * (__uint_as_float(dp[c + 1]) - dlt));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2));
+                        float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2));
+                        if (c >= valid) p0 = 0.f;
+                        if (c + 1 >= valid) p1 = 0.f;
+                        dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt), p1 * (__uint_as_float(dp[c + 1]) - dlt));
+                    }
+                }
+                if (half == 0 && j >= 1) mbar_wait(ds_empty, (j - 1) & 1);   // the dQ MMAs of step j-1 have read dS
+                st_row_chunks(smem_u32(sDS), row, half, dsk);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_full);
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            float v[32];
+            tmem_ld_32x32(tmem_dq + lane_sel + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+            if (qrow < p.S) store_row32_bf16(p.dq + ((long long)b * p.S + qrow) * p.ld_dqkv + h * kTcD + half * 32, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
 // ---------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -952,15 +1325,26 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e;
     static bool attr_done = false;
+    static int use_v2 = 0;
     if (!attr_done) {
         TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
         TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
+        const char* e = getenv("TAVK_ATTN_BWD_V2");    // A/B switch for profiling: the one-CTA-per-SM kernels
+        use_v2 = (e != nullptr && e[0] == '1');
         attr_done = true;
     }
     dim3 grid((a->S + 127) / 128, a->nh, a->B);
-    attn_bwd_dkv_tc_kernel<<<grid, kBwThreads, kDkvSmem, stream>>>(tq64, tk128, tv128, tdo64, d);
-    TAVK_CUDA(cudaGetLastError());
-    attn_bwd_dq_tc_kernel<<<grid, kBwThreads, kDqSmem, stream>>>(tq128, tk64, tv64, tdo128, d);
+    if (use_v2) {
+        attn_bwd_dkv_tc_kernel<<<grid, kBwThreads, kDkvSmem, stream>>>(tq64, tk128, tv128, tdo64, d);
+        TAVK_CUDA(cudaGetLastError());
+        attn_bwd_dq_tc_kernel<<<grid, kBwThreads, kDqSmem, stream>>>(tq128, tk64, tv64, tdo128, d);
+    } else {
+        attn_bwd_dkv_tc2_kernel<<<grid, kB3Threads, kDkv3Smem, stream>>>(tq64, tk128, tv128, tdo64, d);
+        TAVK_CUDA(cudaGetLastError());
+        attn_bwd_dq_tc2_kernel<<<grid, kB3Threads, kDq3Smem, stream>>>(tq128, tk64, tv64, tdo128, d);
+    }
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
