@@ -293,8 +293,14 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down without ncclCommDestroy: the communicator is referenced by the captured step graphs (the bucketed
+        # all-reduces are graph nodes) and NCCL defers / blocks communicator destruction while such graphs are alive,
+        # which hung the 2-GPU run at exit.  Everything is flushed, every rank is past the last collective: leave.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
