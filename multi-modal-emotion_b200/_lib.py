@@ -104,7 +104,7 @@ _lib = None
 launch_count = 0   # library entry points invoked
 kernel_count = 0   # CUDA kernels those entry points launched (bench.py reports it as gpu_launches)
 record_gemms = False
-gemm_log = []      # (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, rowbias, accumulate, k_splits) per launch
+gemm_log = []      # (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, rowbias, accumulate, k_splits, groups) per launch
 # kernels launched per entry point (memset nodes are not counted)
 _KERNELS = {"tavk_attn_bwd": 3, "tavk_groupnorm_gelu_fwd": 2, "tavk_groupnorm_bwd": 2}
 
@@ -182,7 +182,8 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
     if record_gemms:
         gemm_log.append((M, N, K, int(a_mn), int(b_mn), epilogue, int(out.dtype == torch.bfloat16), int(bias is not None),
-                         int(resid is not None), int(rowbias is not None), int(accumulate), k_splits))
+                         int(resid is not None), int(rowbias is not None), int(accumulate), k_splits,
+                         int(ext.get("groups", 1) or 1)))
     call("tavk_gemm_bf16", C.byref(a))
 
 

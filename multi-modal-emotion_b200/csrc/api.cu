@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this library: tavk_device_check() is what the Python host calls at import
 // time on a GPU box, and every compute entry point enqueues sm_100a-only kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tavk.h"
@@ -28,6 +29,18 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        // Off unless TAVK_PDL=1.  Measured on the full step (r1): with the early trigger only in the single-wave GEMM the
+        // step time is unchanged (46.9 vs 46.6 ms) — GEMM->GEMM chains, where it saves 0.9 us per launch, are rare — and
+        // an early trigger in multi-wave kernels hung (see pdl_trigger in common.cuh).
+        const char* e = getenv("TAVK_PDL");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
 }
 
 }  // namespace tavk

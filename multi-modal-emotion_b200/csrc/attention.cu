@@ -127,6 +127,7 @@ struct AttnFwdDev {
 };
 
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnFwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ __align__(128) uint8_t smem[5 * kTileBytes];  // Q | K0 K1 | V0 V1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnFwdDev p) {
 // ---------------------------------------------------------------- backward: delta = rowsum(dO * O)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                   long long ld_o, float* __restrict__ delta, int B, int S, int nh) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     // 8 lanes per (row, head): 8 x 16-byte loads cover the 64-wide head slice
     const long long gid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
@@ -261,6 +263,7 @@ struct AttnBwdDev {
 
 // ---------------------------------------------------------------- backward: dQ (CTA = 64 queries, loops over keys)
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ __align__(128) uint8_t smem[];  // Q | dO | K0 K1 | V0 V1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdDev p) {
 
 // ---------------------------------------------------------------- backward: dK, dV (CTA = 64 keys, loops over queries)
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ __align__(128) uint8_t smem[];  // K | V | Q0 Q1 | dO0 dO1 | lse[2][64] delta[2][64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
@@ -494,7 +498,7 @@ extern "C" int tavk_attn_fwd(const tavk_attn_args* a, void* stream_) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale_log2 = a->scale * kLog2e;
     dim3 grid((a->S + kTile - 1) / kTile, a->nh, a->B);
-    attn_fwd_kernel<<<grid, 128, 0, stream>>>(d);
+    TAVK_CUDA(launch_kernel(attn_fwd_kernel, dim3(grid), dim3(128), (size_t)(0), stream, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -531,8 +535,8 @@ extern "C" int tavk_attn_bwd(const tavk_attn_bwd_args* a, void* stream_) {
     d.scale = a->scale; d.scale_log2 = a->scale * kLog2e;
 
     const long long pairs = (long long)a->B * a->S * a->nh;
-    attn_delta_kernel<<<(int)((pairs * 8 + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(a->o), d.d_o, a->ld_o, a->delta, a->B, a->S, a->nh);
+    TAVK_CUDA(launch_kernel(attn_delta_kernel, dim3((int)((pairs * 8 + 255) / 256)), dim3(256), (size_t)(0), stream, 
+        reinterpret_cast<const __nv_bfloat16*>(a->o), d.d_o, a->ld_o, a->delta, a->B, a->S, a->nh));
     TAVK_CUDA(cudaGetLastError());
 
     if (a->mode == TAVK_ATTN_NONE && a->S >= 128 && use_tc_path()) return attn_bwd_tc_launch(a, stream);
@@ -546,9 +550,9 @@ extern "C" int tavk_attn_bwd(const tavk_attn_bwd_args* a, void* stream_) {
         attr_done = true;
     }
     dim3 grid((a->S + kTile - 1) / kTile, a->nh, a->B);
-    attn_bwd_dkv_kernel<<<grid, 128, kSmemDkv, stream>>>(d);
+    TAVK_CUDA(launch_kernel(attn_bwd_dkv_kernel, dim3(grid), dim3(128), (size_t)(kSmemDkv), stream, d));
     TAVK_CUDA(cudaGetLastError());
-    attn_bwd_dq_kernel<<<grid, 128, kSmemDq, stream>>>(d);
+    TAVK_CUDA(launch_kernel(attn_bwd_dq_kernel, dim3(grid), dim3(128), (size_t)(kSmemDq), stream, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -67,6 +67,7 @@ struct AttnTcDev {
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -294,6 +295,7 @@ constexpr uint32_t kF3TmemCols = 256;
 __global__ void __launch_bounds__(kF3Threads, 2)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -533,6 +535,7 @@ __global__ void __launch_bounds__(kBwThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                        const AttnTcBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -719,6 +722,7 @@ __global__ void __launch_bounds__(kBwThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                       const AttnTcBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -878,6 +882,7 @@ __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                         const AttnTcBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;
@@ -1071,6 +1076,7 @@ __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                        const AttnTcBwdDev p) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -1291,12 +1297,12 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
     if (use_v2) {
-        attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(tq, tk, tv, d);
+        TAVK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(grid), dim3(kTcThreads), (size_t)(kTcSmem), stream, tq, tk, tv, d));
     } else {
         CUtensorMap tk64, tv64;
         if ((rc = make_tmap_bsd(&tk64, a->k, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
         if ((rc = make_tmap_bsd(&tv64, a->v, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
-        attn_fwd_tc64_kernel<<<grid, kF3Threads, kF3Smem, stream>>>(tq, tk64, tv64, d);
+        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
     }
     TAVK_CUDA(cudaGetLastError());
     return 0;
@@ -1337,13 +1343,13 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     }
     dim3 grid((a->S + 127) / 128, a->nh, a->B);
     if (use_v2) {
-        attn_bwd_dkv_tc_kernel<<<grid, kBwThreads, kDkvSmem, stream>>>(tq64, tk128, tv128, tdo64, d);
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDkvSmem), stream, tq64, tk128, tv128, tdo64, d));
         TAVK_CUDA(cudaGetLastError());
-        attn_bwd_dq_tc_kernel<<<grid, kBwThreads, kDqSmem, stream>>>(tq128, tk64, tv64, tdo128, d);
+        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDqSmem), stream, tq128, tk64, tv64, tdo128, d));
     } else {
-        attn_bwd_dkv_tc2_kernel<<<grid, kB3Threads, kDkv3Smem, stream>>>(tq64, tk128, tv128, tdo64, d);
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
         TAVK_CUDA(cudaGetLastError());
-        attn_bwd_dq_tc2_kernel<<<grid, kB3Threads, kDq3Smem, stream>>>(tq128, tk64, tv64, tdo128, d);
+        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
     }
     TAVK_CUDA(cudaGetLastError());
     return 0;

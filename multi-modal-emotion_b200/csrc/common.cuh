@@ -31,6 +31,35 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 int sm_count();
+bool pdl_enabled();   // programmatic dependent launch: opt-in with TAVK_PDL=1 (see api.cu for the measurement)
+
+// Launch with the programmatic-stream-serialization attribute: the grid may be scheduled while its predecessor on the
+// stream is still draining, so its launch latency and its prologue (barrier init, TMEM allocation, descriptor
+// prefetch) overlap the predecessor's tail.  Every kernel launched this way executes pdl_wait() before it touches
+// global memory its predecessor may have written; the dependency is captured as a programmatic edge in CUDA graphs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch (device side)
+// Blocks until the predecessor grid has completed and its memory is visible (no-op without the launch attribute).
+TAVK_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the successor grid start being scheduled (its blocks still stop at their own pdl_wait()).  Used ONLY by kernels
+// whose whole grid is resident at once (the persistent one-CTA-per-SM GEMM): a multi-wave grid that triggers early lets
+// waiting successor blocks take the SMs its own unscheduled blocks still need (observed as a hang).
+TAVK_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- small math
 TAVK_DEVINL float warp_sum(float v) {

@@ -22,6 +22,7 @@ constexpr int kConv0MaxK = 16;
 __global__ void __launch_bounds__(256)
 conv0_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float* __restrict__ bias,
                  __nv_bfloat16* __restrict__ u, int L, int R, int T, int C, int k, int s) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ float sw[];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * 64;
@@ -113,6 +114,7 @@ TAVK_DEVINL void gn_block_accumulate(float (&a0)[8], float (&a1)[8], float* red,
 // bulk, so the one-pass variance does not cancel)
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__ sums, int R, int T, int C) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ float red[8 * 64 * 2];
     const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const __nv_bfloat16* base = u + (size_t)b * R * C + c0 + cg * 8;
@@ -141,6 +143,7 @@ groupnorm_gelu_apply_kernel(const __nv_bfloat16* __restrict__ u, const float* __
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ a, float* __restrict__ mean,
                             float* __restrict__ rstd, int R, int T, int C, float eps) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const int c = c0 + cg * 8;
     const size_t base = (size_t)b * R * C + c;
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u,
                            const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ sums,
                            int R, int T, int C) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ float red[8 * 64 * 2];
     const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const int c = c0 + cg * 8;
@@ -211,6 +215,7 @@ groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bflo
                            const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ sums,
                            __nv_bfloat16* __restrict__ du, int R, int T, int C) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int b = blockIdx.z, c0 = blockIdx.x * 64, cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
     const int c = c0 + cg * 8;
     const size_t base = (size_t)b * R * C + c;
@@ -244,6 +249,7 @@ groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bflo
 // weight-gradient GEMM
 __global__ void wave_windows_kernel(const float* __restrict__ wav, __nv_bfloat16* __restrict__ win, int L, int R, int T,
                                     int k, int s, long long total) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(i & 15);
         const long long row = i >> 4;
@@ -269,8 +275,8 @@ extern "C" int tavk_conv0_fwd(const float* wav, const float* w, const float* bia
     TAVK_CHECK((T - 1) * (long long)s + k <= L, 1, "tavk_conv0_fwd: T=%d frames need more than L=%d samples", T, L);
     dim3 grid((R + 63) / 64, B);
     const size_t smem = (size_t)(63 * s + k) * sizeof(float);
-    conv0_fwd_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        wav, w, bias, reinterpret_cast<__nv_bfloat16*>(u), L, R, T, C, k, s);
+    TAVK_CUDA(launch_kernel(conv0_fwd_kernel, dim3(grid), dim3(256), (size_t)(smem), reinterpret_cast<cudaStream_t>(stream), 
+        wav, w, bias, reinterpret_cast<__nv_bfloat16*>(u), L, R, T, C, k, s));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -283,10 +289,10 @@ extern "C" int tavk_groupnorm_gelu_fwd(const void* u, const float* gamma, const 
     TAVK_CHECK(C % 64 == 0 && R >= T && T > 0 && B > 0, 1, "tavk_groupnorm_gelu_fwd: C %% 64 == 0 required (C=%d)", C);
     TAVK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * 2 * C * sizeof(float), stream));
     dim3 g1(C / 64, (T + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B), g2(C / 64, (R + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B);
-    groupnorm_stats_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, R, T, C);
-    groupnorm_gelu_apply_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, gamma, beta,
+    TAVK_CUDA(launch_kernel(groupnorm_stats_kernel, dim3(g1), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, R, T, C));
+    TAVK_CUDA(launch_kernel(groupnorm_gelu_apply_kernel, dim3(g2), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(u), sums_ws, gamma, beta,
                                                         reinterpret_cast<__nv_bfloat16*>(z),
-                                                        reinterpret_cast<__nv_bfloat16*>(a), mean, rstd, R, T, C, eps);
+                                                        reinterpret_cast<__nv_bfloat16*>(a), mean, rstd, R, T, C, eps));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -299,11 +305,11 @@ extern "C" int tavk_groupnorm_bwd(const void* dz, const void* u, const float* me
     TAVK_CHECK(C % 64 == 0 && R >= T && T > 0 && B > 0, 1, "tavk_groupnorm_bwd: C %% 64 == 0 required (C=%d)", C);
     TAVK_CUDA(cudaMemsetAsync(sums_ws, 0, (size_t)B * 2 * C * sizeof(float), stream));
     dim3 g1(C / 64, (T + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B), g2(C / 64, (R + kGnRowsPerBlock - 1) / kGnRowsPerBlock, B);
-    groupnorm_bwd_stats_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
-                                                       reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, sums_ws, R, T, C);
-    groupnorm_bwd_apply_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
+    TAVK_CUDA(launch_kernel(groupnorm_bwd_stats_kernel, dim3(g1), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(dz),
+                                                       reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, sums_ws, R, T, C));
+    TAVK_CUDA(launch_kernel(groupnorm_bwd_apply_kernel, dim3(g2), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(dz),
                                                        reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, gamma, sums_ws,
-                                                       reinterpret_cast<__nv_bfloat16*>(du), R, T, C);
+                                                       reinterpret_cast<__nv_bfloat16*>(du), R, T, C));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -313,8 +319,8 @@ extern "C" int tavk_wave_windows(const float* wav, void* win, int B, int L, int 
     TAVK_CHECK(k >= 1 && k <= 16 && s >= 1 && B > 0 && R >= T, 1, "tavk_wave_windows: 1 <= k <= 16 (k=%d)", k);
     const long long total = (long long)B * R * 16;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    wave_windows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        wav, reinterpret_cast<__nv_bfloat16*>(win), L, R, T, k, s, total);
+    TAVK_CUDA(launch_kernel(wave_windows_kernel, dim3(blocks), dim3(256), (size_t)(0), reinterpret_cast<cudaStream_t>(stream), 
+        wav, reinterpret_cast<__nv_bfloat16*>(win), L, R, T, k, s, total));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

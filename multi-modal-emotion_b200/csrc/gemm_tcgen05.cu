@@ -314,6 +314,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
     const int num_tiles = p.groups * p.tiles_per_group;
+    pdl_trigger();   // the next kernel on the stream may start its own prologue ...
+    pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
 
     if (warp_idx == 0) {
         // ===================== TMA producer (one thread) =====================
@@ -462,8 +464,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
         TAVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, dev);
-    TAVK_CUDA(cudaGetLastError());
+    TAVK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, dev));
     return 0;
 }
 

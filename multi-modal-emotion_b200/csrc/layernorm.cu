@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, float eps) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     constexpr int H = VEC * 128;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -74,6 +75,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      const float* __restrict__ dx_resid, float* __restrict__ dx_f32,
                      __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dx_colsum, int M) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     constexpr int H = VEC * 128;
     extern __shared__ float red[];  // [warps][H]
     const int lane = threadIdx.x & 31;
@@ -167,7 +169,7 @@ extern "C" int tavk_layernorm_fwd(const float* x, const float* gamma, const floa
     __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
 #define LN_FWD(V)                                                                                              \
     case V:                                                                                                    \
-        layernorm_fwd_kernel<V><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, eps); \
+        TAVK_CUDA(launch_kernel(layernorm_fwd_kernel<V>, dim3(grid), dim3(warps * 32), (size_t)(0), stream, x, gamma, beta, yb, y_f32, mean, rstd, M, eps)); \
         break;
     switch (H / 128) {
         LN_FWD(1) LN_FWD(2) LN_FWD(3) LN_FWD(4) LN_FWD(5) LN_FWD(6) LN_FWD(7) LN_FWD(8)
@@ -194,8 +196,8 @@ extern "C" int tavk_layernorm_bwd(const float* dy, const float* x, const float* 
     __nv_bfloat16* db16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
 #define LN_BWD(V)                                                                                                  \
     case V:                                                                                                        \
-        layernorm_bwd_kernel<V><<<grid, warps * 32, smem, stream>>>(dy, x, mean, rstd, gamma, dx_resid, dx_f32, db16, \
-                                                                   dgamma, dbeta, dx_colsum, M);                   \
+        TAVK_CUDA(launch_kernel(layernorm_bwd_kernel<V>, dim3(grid), dim3(warps * 32), (size_t)(smem), stream, dy, x, mean, rstd, gamma, dx_resid, dx_f32, db16, \
+                                                                   dgamma, dbeta, dx_colsum, M));                   \
         break;
     switch (H / 128) {
         LN_BWD(1) LN_BWD(2) LN_BWD(3) LN_BWD(4) LN_BWD(5) LN_BWD(6) LN_BWD(7) LN_BWD(8)

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256)
 softmax_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
                       const float* __restrict__ cw, float* __restrict__ probs, float* __restrict__ loss_num,
                       float* __restrict__ loss_den, int B, int C) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ float s_num[8], s_den[8];
     float num = 0.f, den = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -47,6 +48,7 @@ softmax_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restric
 __global__ void softmax_ce_bwd_kernel(const float* __restrict__ probs, const int64_t* __restrict__ target,
                                       const float* __restrict__ cw, const float* __restrict__ gscale,
                                       float* __restrict__ dlogits, int B, int C) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
     const int r = i / C, c = i - r * C;
@@ -59,6 +61,7 @@ __global__ void softmax_ce_bwd_kernel(const float* __restrict__ probs, const int
 // ---------------------------------------------------------------- grad norm
 __global__ void __launch_bounds__(256)
 grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ float s_part[8];
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -99,6 +102,7 @@ TAVK_DEVINL float adam_one(float& p, float& m, float& v, float g, const AdamArgs
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
              __nv_bfloat16* __restrict__ p_bf16, long long n, const float* __restrict__ sqnorm, AdamArgs a) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     float gs = a.prescale;
     if (sqnorm != nullptr && a.max_norm > 0.f) {
         // clip_grad_norm_: the norm is taken over the (pre-scaled) gradient
@@ -142,7 +146,7 @@ extern "C" int tavk_softmax_ce_fwd(const float* logits, const int64_t* target, c
                                    float* loss_num, float* loss_den, int B, int C, void* stream) {
     TAVK_CHECK(logits && target && loss_num && loss_den, 1, "tavk_softmax_ce_fwd: null pointer");
     TAVK_CHECK(B >= 0 && C >= 1, 1, "tavk_softmax_ce_fwd: bad shape B=%d C=%d", B, C);
-    softmax_ce_fwd_kernel<<<1, 256, 0, STREAM(stream)>>>(logits, target, class_weight, probs, loss_num, loss_den, B, C);
+    TAVK_CUDA(launch_kernel(softmax_ce_fwd_kernel, dim3(1), dim3(256), (size_t)(0), STREAM(stream), logits, target, class_weight, probs, loss_num, loss_den, B, C));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -152,8 +156,8 @@ extern "C" int tavk_softmax_ce_bwd(const float* probs, const int64_t* target, co
     TAVK_CHECK(probs && target && gscale_dev && dlogits, 1, "tavk_softmax_ce_bwd: null pointer");
     if (B <= 0) return 0;
     const int total = B * C;
-    softmax_ce_bwd_kernel<<<(total + 127) / 128, 128, 0, STREAM(stream)>>>(probs, target, class_weight, gscale_dev,
-                                                                          dlogits, B, C);
+    TAVK_CUDA(launch_kernel(softmax_ce_bwd_kernel, dim3((total + 127) / 128), dim3(128), (size_t)(0), STREAM(stream), probs, target, class_weight, gscale_dev,
+                                                                          dlogits, B, C));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -165,7 +169,7 @@ extern "C" int tavk_grad_sqnorm(const float* g, int64_t n, float* out, void* str
     long long blocks = ((n + 3) / 4 + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    grad_sqnorm_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(g, n, out);
+    TAVK_CUDA(launch_kernel(grad_sqnorm_kernel, dim3((int)blocks), dim3(256), (size_t)(0), STREAM(stream), g, n, out));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -189,8 +193,8 @@ extern "C" int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, 
     long long blocks = ((n + 3) / 4 + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    adamw_kernel<<<(int)blocks, 256, 0, STREAM(stream)>>>(p, m, v, g, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
-                                                          sqnorm_dev, a);
+    TAVK_CUDA(launch_kernel(adamw_kernel, dim3((int)blocks), dim3(256), (size_t)(0), STREAM(stream), p, m, v, g, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
+                                                          sqnorm_dev, a));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,6 +10,7 @@ namespace tavk {
 __global__ void embed_add_fwd_kernel(const float4* __restrict__ x, const int64_t* __restrict__ idx,
                                      const float4* __restrict__ table, float4* __restrict__ y, int rows, int H4,
                                      int n_embed) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long total = (long long)rows * H4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -26,6 +27,7 @@ __global__ void embed_add_fwd_kernel(const float4* __restrict__ x, const int64_t
 // dtable[j, c] += sum over rows with idx == j; block = 256 columns-quads slab, rows chunked over blockIdx.y
 __global__ void embed_add_bwd_kernel(const float* __restrict__ dy, const int64_t* __restrict__ idx,
                                      float* __restrict__ dtable, int rows, int H, int n_embed, int rows_per_chunk) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= H) return;
     const int r0 = blockIdx.y * rows_per_chunk;
@@ -47,6 +49,7 @@ __global__ void embed_add_bwd_kernel(const float* __restrict__ dy, const int64_t
 // ---------------------------------------------------------------- mean pool (models/tav.py:478,481,488)
 __global__ void mean_pool_fwd_kernel(const float4* __restrict__ x, float* __restrict__ y, int S, int H4,
                                      int rows_per_chunk, float inv_s) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= H4) return;
     const int b = blockIdx.z;
@@ -67,6 +70,7 @@ __global__ void mean_pool_fwd_kernel(const float4* __restrict__ x, float* __rest
 
 __global__ void mean_pool_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx,
                                      uint2* __restrict__ dx_bf16, int S, int H4, long long total, float inv_s) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / H4;
@@ -84,6 +88,7 @@ __global__ void mean_pool_bwd_kernel(const float4* __restrict__ dy, float4* __re
 template <bool BF16>
 __global__ void colsum_kernel(const void* __restrict__ x_, long long ld, const float* __restrict__ w,
                               float* __restrict__ out, int S, int N, int rows_per_chunk) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
     if (c4 * 4 >= N) return;
     const int b = blockIdx.z;
@@ -140,8 +145,8 @@ static int launch_colsum(const void* x, int x_dtype, long long ld, const float* 
     if (rows_per_chunk < 8) rows_per_chunk = 8;
     chunks = (S + rows_per_chunk - 1) / rows_per_chunk;
     dim3 grid(gx, chunks, B);
-    if (x_dtype == TAVK_BF16) colsum_kernel<true><<<grid, threads, 0, stream>>>(x, ld, w, out, S, N, rows_per_chunk);
-    else                      colsum_kernel<false><<<grid, threads, 0, stream>>>(x, ld, w, out, S, N, rows_per_chunk);
+    if (x_dtype == TAVK_BF16) TAVK_CUDA(launch_kernel(colsum_kernel<true>, dim3(grid), dim3(threads), (size_t)(0), stream, x, ld, w, out, S, N, rows_per_chunk));
+    else                      TAVK_CUDA(launch_kernel(colsum_kernel<false>, dim3(grid), dim3(threads), (size_t)(0), stream, x, ld, w, out, S, N, rows_per_chunk));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -150,6 +155,7 @@ static int launch_colsum(const void* x, int x_dtype, long long ld, const float* 
 // y[m,n] = sum_k x[m,k] w[n,k] + b[n]; one warp per output element.
 __global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                         const float* __restrict__ b, float* __restrict__ y, int M, int N, int K) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const int lane = threadIdx.x & 31;
     const long long o = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (o >= (long long)M * N) return;
@@ -173,6 +179,7 @@ __global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float
 // partial sums combined with one atomic per thread (dx is zeroed by the host wrapper unless accumulating)
 __global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                           float* __restrict__ dx, int M, int N, int K, int n_per_chunk) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)M * K) return;
     const int m = (int)(i / K), k = (int)(i - (long long)m * K);
@@ -193,6 +200,7 @@ __global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, const fl
 // dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n,k)
 __global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                           float* __restrict__ dw, float* __restrict__ db, int M, int N, int K) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= (long long)N * K) return;
     const int n = (int)(i / K), k = (int)(i - (long long)n * K);
@@ -208,6 +216,7 @@ __global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, const fl
 
 // ---------------------------------------------------------------- casts / scaling / dropout
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -218,6 +227,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
     for (long long i = (n4 << 2) + t; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
 }
 __global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict__ y, float scale, long long n) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) y[i] = x[i] * scale;
 }
@@ -232,6 +242,7 @@ TAVK_DEVINL float uniform01(uint64_t seed, uint64_t ctr) {
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ keep,
                                    long long n, float p, float inv_keep, uint64_t seed, uint64_t offset,
                                    const uint64_t* __restrict__ offset_dev) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     if (offset_dev != nullptr) offset += (*offset_dev) << 32;  // device-side step counter (CUDA-graph replays)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -242,6 +253,7 @@ __global__ void dropout_fwd_kernel(const float* __restrict__ x, float* __restric
 }
 __global__ void dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ keep,
                                    float* __restrict__ dx, long long n, float inv_keep) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
         dx[i] = keep[i] ? dy[i] * inv_keep : 0.f;
@@ -251,6 +263,7 @@ __global__ void dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
 // via a 32x32 smem transpose of the (S, d) plane of every (b, h); `inverse` maps back (used in backward).
 __global__ void permute_bshd_bhds_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int S,
                                          int nh, int d, int inverse) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
     __shared__ __nv_bfloat16 tile[32][33];
     const int bh = blockIdx.z;
     const int b = bh / nh, h = bh % nh;
@@ -298,9 +311,9 @@ extern "C" int tavk_embed_add_fwd(const float* x, const int64_t* idx, const floa
     TAVK_CHECK(H % 4 == 0 && n_embed >= 1, 1, "tavk_embed_add_fwd: H=%d must be a multiple of 4", H);
     if (rows <= 0) return 0;
     const long long total = (long long)rows * (H / 4);
-    embed_add_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+    TAVK_CUDA(launch_kernel(embed_add_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), STREAM(stream), 
         reinterpret_cast<const float4*>(x), idx, reinterpret_cast<const float4*>(table), reinterpret_cast<float4*>(y),
-        rows, H / 4, n_embed);
+        rows, H / 4, n_embed));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -316,7 +329,7 @@ extern "C" int tavk_embed_add_bwd(const float* dy, const int64_t* idx, float* dt
     int rpc = (rows + chunks - 1) / chunks;
     if (rpc < 16) rpc = 16;
     chunks = (rows + rpc - 1) / rpc;
-    embed_add_bwd_kernel<<<dim3(gx, chunks), threads, 0, STREAM(stream)>>>(dy, idx, dtable, rows, H, n_embed, rpc);
+    TAVK_CUDA(launch_kernel(embed_add_bwd_kernel, dim3(dim3(gx, chunks)), dim3(threads), (size_t)(0), STREAM(stream), dy, idx, dtable, rows, H, n_embed, rpc));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -334,8 +347,8 @@ extern "C" int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H,
     int rpc = (S + chunks - 1) / chunks;
     if (rpc < 8) rpc = 8;
     chunks = (S + rpc - 1) / rpc;
-    mean_pool_fwd_kernel<<<dim3(gx, chunks, B), threads, 0, STREAM(stream)>>>(reinterpret_cast<const float4*>(x), y, S,
-                                                                            H / 4, rpc, 1.0f / (float)S);
+    TAVK_CUDA(launch_kernel(mean_pool_fwd_kernel, dim3(dim3(gx, chunks, B)), dim3(threads), (size_t)(0), STREAM(stream), reinterpret_cast<const float4*>(x), y, S,
+                                                                            H / 4, rpc, 1.0f / (float)S));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -345,9 +358,9 @@ extern "C" int tavk_mean_pool_bwd(const float* dy, float* dx, void* dx_bf16, int
     TAVK_CHECK(H % 4 == 0, 1, "tavk_mean_pool_bwd: H=%d must be a multiple of 4", H);
     if (B <= 0 || S <= 0) return 0;
     const long long total = (long long)B * S * (H / 4);
-    mean_pool_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(
+    TAVK_CUDA(launch_kernel(mean_pool_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), STREAM(stream), 
         reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), reinterpret_cast<uint2*>(dx_bf16), S, H / 4,
-        total, 1.0f / (float)S);
+        total, 1.0f / (float)S));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -370,7 +383,7 @@ extern "C" int tavk_small_linear_fwd(const float* x, const float* w, const float
     const int threads = 256;
     const long long grid = (threads_total + threads - 1) / threads;
     TAVK_CHECK(grid < (1ll << 31), 2, "tavk_small_linear_fwd: problem too large for this kernel");
-    small_linear_fwd_kernel<<<(int)grid, threads, 0, STREAM(stream)>>>(x, w, b, y, M, N, K);
+    TAVK_CUDA(launch_kernel(small_linear_fwd_kernel, dim3((int)grid), dim3(threads), (size_t)(0), STREAM(stream), x, w, b, y, M, N, K));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -387,7 +400,7 @@ extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* d
     int npc = (N + chunks - 1) / chunks;
     if (npc < 8) npc = 8;
     chunks = (N + npc - 1) / npc;
-    small_linear_bwd_x_kernel<<<dim3(gx, chunks), 128, 0, STREAM(stream)>>>(dy, w, dx, M, N, K, npc);
+    TAVK_CUDA(launch_kernel(small_linear_bwd_x_kernel, dim3(dim3(gx, chunks)), dim3(128), (size_t)(0), STREAM(stream), dy, w, dx, M, N, K, npc));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -397,7 +410,7 @@ extern "C" int tavk_small_linear_bwd_w(const float* dy, const float* x, float* d
     TAVK_CHECK(dy && x && (dw || db), 1, "tavk_small_linear_bwd_w: null pointer");
     if (N <= 0 || K <= 0) return 0;
     const long long total = (long long)N * K;
-    small_linear_bwd_w_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(dy, x, dw, db, M, N, K);
+    TAVK_CUDA(launch_kernel(small_linear_bwd_w_kernel, dim3((int)((total + 127) / 128)), dim3(128), (size_t)(0), STREAM(stream), dy, x, dw, db, M, N, K));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -407,8 +420,8 @@ extern "C" int tavk_cast_f32_bf16(const float* x, void* y, int64_t n, void* stre
     TAVK_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, 1,
                "tavk_cast_f32_bf16: buffers must be 16/8-byte aligned");
     if (n <= 0) return 0;
-    cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, STREAM(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(y),
-                                                                                 n);
+    TAVK_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), STREAM(stream), x, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                                 n));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -416,7 +429,7 @@ extern "C" int tavk_cast_f32_bf16(const float* x, void* y, int64_t n, void* stre
 extern "C" int tavk_scale_f32(const float* x, float* y, float scale, int64_t n, void* stream) {
     TAVK_CHECK(x && y, 1, "tavk_scale_f32: null pointer");
     if (n <= 0) return 0;
-    scale_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, y, scale, n);
+    TAVK_CUDA(launch_kernel(scale_f32_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), STREAM(stream), x, y, scale, n));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -426,8 +439,8 @@ extern "C" int tavk_dropout(const float* x, float* y, uint8_t* keep_mask, int64_
     TAVK_CHECK(x && y && keep_mask, 1, "tavk_dropout: null pointer");
     TAVK_CHECK(p >= 0.f && p < 1.f, 1, "tavk_dropout: p=%f out of [0,1)", (double)p);
     if (n <= 0) return 0;
-    dropout_fwd_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(x, y, keep_mask, n, p, 1.0f / (1.0f - p), seed,
-                                                                     offset, offset_dev);
+    TAVK_CUDA(launch_kernel(dropout_fwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), STREAM(stream), x, y, keep_mask, n, p, 1.0f / (1.0f - p), seed,
+                                                                     offset, offset_dev));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -436,7 +449,7 @@ extern "C" int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float
                                 void* stream) {
     TAVK_CHECK(dy && dx && keep_mask, 1, "tavk_dropout_bwd: null pointer");
     if (n <= 0) return 0;
-    dropout_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(dy, keep_mask, dx, n, 1.0f / (1.0f - p));
+    TAVK_CUDA(launch_kernel(dropout_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), STREAM(stream), dy, keep_mask, dx, n, 1.0f / (1.0f - p)));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -446,9 +459,9 @@ extern "C" int tavk_permute_bshd_bhds(const void* in, void* out, int B, int S, i
     TAVK_CHECK(in && out, 1, "tavk_permute_bshd_bhds: null pointer");
     if (B <= 0 || S <= 0) return 0;
     dim3 grid((S + 31) / 32, (d + 31) / 32, B * nh);
-    permute_bshd_bhds_kernel<<<grid, dim3(32, 8), 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+    TAVK_CUDA(launch_kernel(permute_bshd_bhds_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(in),
                                                                        reinterpret_cast<__nv_bfloat16*>(out), S, nh, d,
-                                                                       inverse);
+                                                                       inverse));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -43,38 +43,90 @@ PARAM_SLOTS = ("ln1_w", "ln1_b", "wq", "wk", "wv", "bq", "bk", "bv", "wo", "bo",
 N_SLOTS = len(PARAM_SLOTS)
 
 
+def _flat_shadow(t):
+    """(bf16 view of parameter `t` inside its optimiser's flat shadow buffer, offset) or (None, None)."""
+    ref = getattr(t, "_tavk_flat", None)
+    if ref is None:
+        return None, None
+    flat, off = ref
+    if flat.shadow is None or t.data_ptr() != flat.flat.data_ptr() + 4 * off:
+        return None, None          # the parameter was re-pointed elsewhere since FlatParams was built
+    return flat.shadow_view(t, off), off
+
+
 class LayerShadow:
-    """bf16 operand copies of one layer's matrices + packed fp32 QKV bias."""
+    """bf16 operand copies of one layer's matrices + packed fp32 QKV bias.
+
+    Two regimes.  Before the fused optimiser exists (or for parameters it does not own) the copies are private buffers,
+    re-cast whenever a parameter's version counter or the optimiser generation changes.  Once optim.FlatParams owns
+    the parameters, the AdamW kernel writes a bf16 mirror of the whole flat buffer in its update pass and the copies
+    are views of that mirror (Q, K, V as one [3H, H] view when their slices are adjacent): nothing is cast per step;
+    only a direct write to a parameter (version counter) triggers a re-cast of its slice."""
 
     def __init__(self):
         self.key = None
         self.wqkv = self.wo = self.w1 = self.w2 = self.bqkv = None
+        self.own = {}
+
+    def _own(self, name, shape, dev):
+        t = self.own.get(name)
+        if t is None or t.shape != shape:
+            t = self.own[name] = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+        return t
 
     def refresh(self, p, spec):
         H = spec.hidden
-        key = (_generation,) + tuple((t.data_ptr(), t._version) if t is not None else None for t in p)
-        if key == self.key:
-            return self
-        dev = p[2].device
-        if self.wqkv is None:
-            self.wqkv = torch.empty((3 * H, H), dtype=torch.bfloat16, device=dev)
-            self.wo = torch.empty((H, H), dtype=torch.bfloat16, device=dev)
-            self.w1 = torch.empty((spec.inter, H), dtype=torch.bfloat16, device=dev)
-            self.w2 = torch.empty((H, spec.inter), dtype=torch.bfloat16, device=dev)
-            self.bqkv = torch.zeros((3 * H,), dtype=torch.float32, device=dev)
         d = dict(zip(PARAM_SLOTS, p))
-        with torch.no_grad():
-            for i, n in enumerate(("wq", "wk", "wv")):
-                L.cast_bf16(d[n].detach(), self.wqkv[i * H:(i + 1) * H])
-            L.cast_bf16(d["wo"].detach(), self.wo)
-            L.cast_bf16(d["w1"].detach(), self.w1)
-            L.cast_bf16(d["w2"].detach(), self.w2)
-            for i, n in enumerate(("bq", "bk", "bv")):
-                if d[n] is not None:
-                    self.bqkv[i * H:(i + 1) * H].copy_(d[n].detach())
+        dev = d["wq"].device
+        mats = ("wq", "wk", "wv", "wo", "w1", "w2")
+        views = {n: _flat_shadow(d[n]) for n in mats}
+        flat_all = all(v[0] is not None for v in views.values())
+        ver = tuple((t.data_ptr(), t._version) if t is not None else None for t in p)
+        key = (flat_all, ver) if flat_all else (flat_all, _generation, ver)
+        bias_key = (_generation, ver)
+        if key != self.key:
+            with torch.no_grad():
+                if flat_all:
+                    # the mirror is kept current by the optimiser (raw-pointer updates do not touch version counters);
+                    # re-cast only a slice whose parameter was written directly since the mirror last matched it
+                    for n in mats:
+                        if d[n]._version != getattr(d[n], "_tavk_mirror_version", None):
+                            L.cast_bf16(d[n].detach(), views[n][0])
+                            d[n]._tavk_mirror_version = d[n]._version
+                    oq, ok, ov = views["wq"][1], views["wk"][1], views["wv"][1]
+                    if ok - oq == H * H and ov - ok == H * H:
+                        self.wqkv = d["wq"]._tavk_flat[0].shadow[oq:oq + 3 * H * H].view(3 * H, H)
+                        self._qkv_views = None
+                    else:
+                        self.wqkv = self._own("wqkv", (3 * H, H), dev)
+                        self._qkv_views = [views[n][0] for n in ("wq", "wk", "wv")]
+                    self.wo, self.w1, self.w2 = views["wo"][0], views["w1"][0], views["w2"][0]
                 else:
-                    self.bqkv[i * H:(i + 1) * H].zero_()
-        self.key = key
+                    self._qkv_views = None
+                    self.wqkv = self._own("wqkv", (3 * H, H), dev)
+                    self.wo = self._own("wo", (H, H), dev)
+                    self.w1 = self._own("w1", (spec.inter, H), dev)
+                    self.w2 = self._own("w2", (H, spec.inter), dev)
+                    for i, n in enumerate(("wq", "wk", "wv")):
+                        L.cast_bf16(d[n].detach(), self.wqkv[i * H:(i + 1) * H])
+                    L.cast_bf16(d["wo"].detach(), self.wo)
+                    L.cast_bf16(d["w1"].detach(), self.w1)
+                    L.cast_bf16(d["w2"].detach(), self.w2)
+            self.key = key
+        if bias_key != getattr(self, "bias_key", None):
+            with torch.no_grad():
+                if getattr(self, "_qkv_views", None) is not None:
+                    # Q, K, V live apart in the flat buffer (biases in between): gather the three bf16 slices
+                    for i, v in enumerate(self._qkv_views):
+                        self.wqkv[i * H:(i + 1) * H].copy_(v)
+                if self.bqkv is None:
+                    self.bqkv = torch.zeros((3 * H,), dtype=torch.float32, device=dev)
+                for i, n in enumerate(("bq", "bk", "bv")):
+                    if d[n] is not None:
+                        self.bqkv[i * H:(i + 1) * H].copy_(d[n].detach())
+                    else:
+                        self.bqkv[i * H:(i + 1) * H].zero_()
+            self.bias_key = bias_key
         return self
 
 

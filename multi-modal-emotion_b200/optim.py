@@ -42,6 +42,16 @@ class FlatParams:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                p._tavk_flat = (self, o)     # lets engine.LayerShadow find the bf16 shadow of this parameter
+        # bf16 mirror of the whole parameter buffer: written by the AdamW kernel in the same pass as the fp32 update, so the
+        # GEMM operand copies ("shadows") of the layer engine are plain views of it — no per-step cast kernels
+        self.shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
+        L.call("tavk_cast_f32_bf16", self.flat.data_ptr(), self.shadow.data_ptr(), off)
+        for p in uniq:
+            p._tavk_mirror_version = p._version
+
+    def shadow_view(self, p, offset):
+        return self.shadow[offset:offset + p.numel()].view(p.shape)
 
     def attach_grads(self):
         """(Re-)point .grad at the flat buffer (after someone set grads to None)."""
@@ -102,7 +112,7 @@ class FusedAdamW(torch.optim.Optimizer):
             L.call("tavk_grad_sqnorm", self.flat.grad.data_ptr(), self.flat.numel, self.sqnorm.data_ptr())
             sq_ptr = self.sqnorm.data_ptr()
         L.call("tavk_adamw", self.flat.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-               self.flat.grad.data_ptr(), None, self.flat.numel, float(g["lr"]), float(g["betas"][0]),
+               self.flat.grad.data_ptr(), self.flat.shadow.data_ptr(), self.flat.numel, float(g["lr"]), float(g["betas"][0]),
                float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.step_count, sq_ptr,
                float(clip) if clip else 0.0, float(self.grad_prescale), 1)
         engine.invalidate_shadows()  # parameters changed behind torch's version counters

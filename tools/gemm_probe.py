@@ -26,7 +26,16 @@ SHAPES = {  # name: (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, k_spl
     "fusion_out_proj": (5168, 768, 768, 0, 0, 0, 0, 1, 1, 1),
     "roberta_out_proj": (1120, 768, 768, 0, 0, 0, 0, 1, 1, 1),
     "posconv": (2384, 48, 6144, 0, 0, 0, 0, 1, 0, 1),
+    "roberta_ffn_down": (1120, 768, 3072, 0, 0, 0, 0, 1, 1, 1),
+    "roberta_ffn_up_gelu": (1120, 3072, 768, 0, 0, L.EPI_GELU, 1, 1, 0, 1),
+    "roberta_qkv": (1120, 2304, 768, 0, 0, 0, 1, 1, 0, 1),
+    "w2v_ffn_down": (2384, 768, 3072, 0, 0, 0, 0, 1, 1, 1),
+    "w2v_ffn_up_gelu": (2384, 3072, 768, 0, 0, L.EPI_GELU, 1, 1, 0, 1),
+    "w2v_out_proj": (2384, 768, 768, 0, 0, 0, 0, 1, 1, 1),
+    "fusion_ffn_down": (5168, 768, 3072, 0, 0, 0, 0, 1, 1, 1),
+    "fusion_qkv": (5168, 2304, 768, 0, 0, 0, 1, 1, 0, 1),
 }
+BLOCK_N = int(os.environ.get("TAVK_PROBE_BLOCK_N", "0"))
 
 
 def run(name, reps):
@@ -34,7 +43,8 @@ def run(name, reps):
     A = torch.randn((k, m) if a_mn else (m, k), device="cuda").bfloat16()
     B = torch.randn((k, n) if b_mn else (n, k), device="cuda").bfloat16()
     out = torch.zeros((m, n), device="cuda", dtype=torch.bfloat16 if obf else torch.float32)
-    kw = dict(M=m, N=n, K=k, a_mn=bool(a_mn), b_mn=bool(b_mn), epilogue=epi, accumulate=ks > 1 or (a_mn and b_mn), k_splits=ks)
+    kw = dict(M=m, N=n, K=k, a_mn=bool(a_mn), b_mn=bool(b_mn), epilogue=epi, accumulate=ks > 1 or (a_mn and b_mn), k_splits=ks,
+              block_n=BLOCK_N)
     if hb:
         kw["bias"] = torch.zeros(n, device="cuda")
     if hr:
@@ -52,7 +62,7 @@ def run(name, reps):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print("%-24s M=%d N=%d K=%d  %.4f ms  %.1f TFLOP/s" % (name, m, n, k, ms, 2.0 * m * n * k / ms / 1e9))
+    print("%-24s M=%d N=%d K=%d bn=%d  %.4f ms  %.1f TFLOP/s" % (name, m, n, k, BLOCK_N, ms, 2.0 * m * n * k / ms / 1e9))
 
 
 if __name__ == "__main__":
