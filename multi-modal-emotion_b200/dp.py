@@ -174,23 +174,70 @@ class DataParallelTAV:
             out = self._eager_step(st_in, st_lab, epoch, check)
         return {"graph": g, "inputs": st_in, "labels": st_lab, "loss": out}
 
-    def train_step(self, inputs, labels, epoch=1, check="train"):
-        """One optimisation step on this rank's shard.  Returns the GLOBAL loss as a device scalar."""
+    def train_step(self, inputs, labels, epoch=1, check="train", next_batch=None):
+        """One optimisation step on this rank's shard.  Returns the GLOBAL loss as a device scalar.
+
+        ``next_batch=(inputs, labels)`` (graph mode, host tensors): the batch the NEXT call will be given.  Its
+        host-to-device copy is started on a copy stream into a staging set right after this step's graph launch, so it
+        overlaps the step's compute (the reference's DataLoader hands batches over one at a time and copies them
+        synchronously, tav_train.py:15-40).  The next call recognises the batch by identity and only moves it
+        device-to-device into the graph's static input buffers."""
         if not self.use_cuda_graph:
             return self._eager_step(inputs, labels, epoch, check)
         key = self._graph_key(inputs, labels, epoch, check)
         if self._graph is None or self._graph["key"] != key:
             self._graph = self._build_graph(inputs, labels, epoch, check)
             self._graph["key"] = key
+            self._staged = None
         st = self._graph
-        for d, sd in zip(inputs, st["inputs"]):
-            for k, v in d.items():
-                if sd[k].data_ptr() != v.data_ptr():
-                    sd[k].copy_(v, non_blocking=True)
-        if st["labels"].data_ptr() != labels.data_ptr():
-            st["labels"].copy_(labels, non_blocking=True)
+        staged = getattr(self, "_staged", None)
+        if staged is not None and staged["id"] == self._batch_id(inputs, labels):
+            torch.cuda.current_stream().wait_event(staged["ready"])
+            for sd, gd in zip(staged["inputs"], st["inputs"]):
+                for k, v in sd.items():
+                    gd[k].copy_(v, non_blocking=True)
+            st["labels"].copy_(staged["labels"], non_blocking=True)
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record()
+        else:
+            for d, sd in zip(inputs, st["inputs"]):
+                for k, v in d.items():
+                    if sd[k].data_ptr() != v.data_ptr():
+                        sd[k].copy_(v, non_blocking=True)
+            if st["labels"].data_ptr() != labels.data_ptr():
+                st["labels"].copy_(labels, non_blocking=True)
+        self._staged = None
         st["graph"].replay()
+        if next_batch is not None:
+            self._stage(next_batch[0], next_batch[1])
         return st["loss"]
+
+    @staticmethod
+    def _batch_id(inputs, labels):
+        return tuple(v.data_ptr() for d in inputs for v in d.values()) + (labels.data_ptr(),)
+
+    def _stage(self, inputs, labels):
+        """Start the H2D copy of the next batch on the copy stream (pinned host memory makes it asynchronous)."""
+        st = self._graph
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_bufs = ([{k: torch.empty_like(v) for k, v in d.items()} for d in st["inputs"]],
+                                torch.empty_like(st["labels"]))
+            self._staging_free = None
+        if tuple((k, tuple(v.shape), v.dtype) for d in inputs for k, v in d.items()) != st["key"][0]:
+            return                                   # different shapes: the next call rebuilds the graph anyway
+        cs = self._copy_stream
+        if self._staging_free is not None:
+            cs.wait_event(self._staging_free)        # the previous staged batch has been moved out of the staging set
+        with torch.cuda.stream(cs):
+            for d, sd in zip(inputs, self._stage_bufs[0]):
+                for k, v in d.items():
+                    sd[k].copy_(v, non_blocking=True)
+            self._stage_bufs[1].copy_(labels, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        self._staged = {"id": self._batch_id(inputs, labels), "inputs": self._stage_bufs[0], "labels": self._stage_bufs[1],
+                        "ready": ready}
 
     def static_inputs(self):
         """Device-resident input buffers of the captured step (write into them to skip the host copy)."""
