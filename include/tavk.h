@@ -132,6 +132,9 @@ typedef struct tavk_attn_bwd_args {
     int32_t B, S, nh;
     int32_t mode;
     float scale;
+    /* optional f32 [nh*64] each: += column sums of dq / dk / dv over all B*S rows — the q/k/v projection bias
+     * gradients — accumulated in the backward kernels' epilogues (tensor-core path) or by column-sum passes (v1) */
+    float* dbq; float* dbk; float* dbv;
 } tavk_attn_bwd_args;
 int tavk_attn_bwd(const tavk_attn_bwd_args* args, void* stream);
 

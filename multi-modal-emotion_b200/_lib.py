@@ -59,6 +59,7 @@ class AttnBwdArgs(C.Structure):
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_dqkv", C.c_int64),
         ("dv_rowscale", C.c_void_p), ("dv_rank1", C.c_void_p),
         ("B", C.c_int32), ("S", C.c_int32), ("nh", C.c_int32), ("mode", C.c_int32), ("scale", C.c_float),
+        ("dbq", C.c_void_p), ("dbk", C.c_void_p), ("dbv", C.c_void_p),
     ]
 
 
@@ -198,7 +199,7 @@ def attn_fwd(q, k, v, o, lse, *, B, S, nh, ld_qkv, ld_o, key_bias=None, scale=0.
 
 
 def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, *, B, S, nh, ld_qkv, ld_o, ld_dqkv, key_bias=None,
-             dv_rowscale=None, dv_rank1=None, scale=0.125):
+             dv_rowscale=None, dv_rank1=None, scale=0.125, dbq=None, dbk=None, dbv=None):
     a = AttnBwdArgs()
     a.q, a.k, a.v, a.ld_qkv = q.data_ptr(), k.data_ptr(), v.data_ptr(), ld_qkv
     a.o, a.d_o, a.ld_o = o.data_ptr(), d_o.data_ptr(), ld_o
@@ -208,6 +209,7 @@ def attn_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, *, B, S, nh, ld_qkv, ld_o,
     a.B, a.S, a.nh = B, S, nh
     a.mode = ATTN_KEY_BIAS if key_bias is not None else ATTN_NONE
     a.scale = scale
+    a.dbq, a.dbk, a.dbv = _ptr(dbq), _ptr(dbk), _ptr(dbv)
     call("tavk_attn_bwd", C.byref(a))
 
 

@@ -463,6 +463,7 @@ static int check_common(const void* q, const void* k, const void* v, long long l
 // attention_tc.cu: tcgen05/TMEM kernels (mask-free mode)
 int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream);
 int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream);
+int attn_bias_grads_by_colsum(const tavk_attn_bwd_args* a, cudaStream_t stream);
 
 // TAVK_ATTN_IMPL=legacy forces the mma.sync kernels everywhere (A/B testing); default: tcgen05 where it applies
 static bool use_tc_path() {
@@ -554,5 +555,5 @@ extern "C" int tavk_attn_bwd(const tavk_attn_bwd_args* a, void* stream_) {
     TAVK_CUDA(cudaGetLastError());
     TAVK_CUDA(launch_kernel(attn_bwd_dq_kernel, dim3(grid), dim3(128), (size_t)(kSmemDq), stream, d));
     TAVK_CUDA(cudaGetLastError());
-    return 0;
+    return attn_bias_grads_by_colsum(a, stream);
 }

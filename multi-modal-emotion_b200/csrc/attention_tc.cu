@@ -518,6 +518,7 @@ struct AttnTcBwdDev {
     const float *dv_rowscale, *dv_rank1;
     int B, S, nh;
     float scale, scale_log2;
+    float *dbq, *dbk, *dbv;      // optional bias-gradient accumulators (column sums of dq / dk / dv), f32 [nh*64]
 };
 
 // 32 packed-pair registers (= 64 bf16... here 16 regs = 32 bf16) -> this row's 4 swizzled 16-byte chunks
@@ -1053,15 +1054,17 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             tmem_ld_32x32(tmem_dk + lane_sel + half * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+            for (int c = 0; c < 32; ++c) v[c] = key < p.S ? __uint_as_float(r[c]) * p.scale : 0.f;
             if (key < p.S) store_row32_bf16(p.dk + out_off, v);
+            if (p.dbk != nullptr) atomicAdd(p.dbk + h * kTcD + half * 32 + lane, warp_colsum32(v, lane));
             // dV (+ rank-1 term of the post-softmax mask: dV[b,k,h,:] += m[b,k] * dc[b,h,:])
             tmem_ld_32x32(tmem_dv + lane_sel + half * 32, r);
             tmem_ld_wait();
             const float* dc = rank1 ? p.dv_rank1 + ((long long)b * p.nh + h) * kTcD + half * 32 : nullptr;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) + (dc ? w * __ldg(dc + c) : 0.f);
+            for (int c = 0; c < 32; ++c) v[c] = key < p.S ? __uint_as_float(r[c]) + (dc ? w * __ldg(dc + c) : 0.f) : 0.f;
             if (key < p.S) store_row32_bf16(p.dv + out_off, v);
+            if (p.dbv != nullptr) atomicAdd(p.dbv + h * kTcD + half * 32 + lane, warp_colsum32(v, lane));
         }
     }
     tc_fence_before();
@@ -1228,8 +1231,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             tmem_ld_32x32(tmem_dq + lane_sel + half * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
+            for (int c = 0; c < 32; ++c) v[c] = qrow < p.S ? __uint_as_float(r[c]) * p.scale : 0.f;
             if (qrow < p.S) store_row32_bf16(p.dq + ((long long)b * p.S + qrow) * p.ld_dqkv + h * kTcD + half * 32, v);
+            if (p.dbq != nullptr) atomicAdd(p.dbq + h * kTcD + half * 32 + lane, warp_colsum32(v, lane));
         }
     }
     tc_fence_before();
@@ -1308,6 +1312,20 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     return 0;
 }
 
+// Bias gradients for the kernels that do not accumulate them in their epilogue (v1 mma.sync path, v2 A/B kernels): one
+// column-sum pass per requested vector over the dq / dk / dv just written.
+int attn_bias_grads_by_colsum(const tavk_attn_bwd_args* a, cudaStream_t stream) {
+    const int M = a->B * a->S, N = a->nh * kTcD;
+    const void* src[3] = {a->dq, a->dk, a->dv};
+    float* dst[3] = {a->dbq, a->dbk, a->dbv};
+    for (int i = 0; i < 3; ++i) {
+        if (dst[i] == nullptr) continue;
+        const int rc = tavk_colsum(src[i], TAVK_BF16, a->ld_dqkv, dst[i], M, N, 1, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // delta must already hold rowsum(dO * O) (attention.cu: attn_delta_kernel)
 int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     CUtensorMap tq64, tk64, tv64, tdo64, tq128, tk128, tv128, tdo128;
@@ -1330,6 +1348,7 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     d.dv_rowscale = a->dv_rowscale; d.dv_rank1 = a->dv_rank1;
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e;
+    d.dbq = a->dbq; d.dbk = a->dbk; d.dbv = a->dbv;
     static bool attr_done = false;
     static int use_v2 = 0;
     if (!attr_done) {
@@ -1346,6 +1365,7 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
         TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDkvSmem), stream, tq64, tk128, tv128, tdo64, d));
         TAVK_CUDA(cudaGetLastError());
         TAVK_CUDA(launch_kernel(attn_bwd_dq_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDqSmem), stream, tq128, tk64, tv64, tdo128, d));
+        return attn_bias_grads_by_colsum(a, stream);
     } else {
         TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
         TAVK_CUDA(cudaGetLastError());

@@ -67,6 +67,21 @@ TAVK_DEVINL float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Column sums of a 32x32 block held as "lane = row, v[c] = column c": recursive halving, 31 shuffles; lane c returns
+// the sum of column c (v is destroyed).
+TAVK_DEVINL float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float send = upper ? v[i] : v[i + o];
+            const float keep = upper ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
 TAVK_DEVINL float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -247,16 +247,20 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
     return z_f32, z_bf, sv
 
 
-def _attention_bwd(spec, sv, do, B, S, mask2d, dc):
+def _attention_bwd(spec, sv, do, B, S, mask2d, dc, go=None):
+    """dqkv [M, 3H] bf16; when ``go`` is given the q/k/v projection bias gradients (column sums of dq/dk/dv) are
+    accumulated into its targets by the backward kernels themselves."""
     H, nh = spec.hidden, spec.heads
     dev = do.device
     dqkv = _bf16((B * S, 3 * H), dev)
     delta = _f32((B, nh, S), dev)
     qkv = sv.qkv
+    db = {n: (go.target(n) if go is not None else None) for n in ("bq", "bk", "bv")}
     L.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv.o, do, sv.lse, delta, dqkv[:, :H], dqkv[:, H:2 * H],
                dqkv[:, 2 * H:], B=B, S=S, nh=nh, ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H,
                key_bias=mask2d if spec.mask_mode == "key_bias" else None,
-               dv_rowscale=mask2d if dc is not None else None, dv_rank1=dc, scale=(H // nh) ** -0.5)
+               dv_rowscale=mask2d if dc is not None else None, dv_rank1=dc, scale=(H // nh) ** -0.5,
+               dbq=db["bq"], dbk=db["bk"], dbv=db["bv"])
     return dqkv
 
 
@@ -288,8 +292,9 @@ class _GradOut:
 
 
 def _qkv_grads(go, dqkv, x_bf, H, M):
-    """dW_q/k/v and db_q/k/v from the packed dqkv [M, 3H]: one [3H, H] wgrad GEMM when the three weight-gradient
-    targets are adjacent in memory (flat-buffer order q, k, v), else one GEMM per matrix."""
+    """dW_q/k/v from the packed dqkv [M, 3H]: one [3H, H] wgrad GEMM when the three weight-gradient targets are
+    adjacent in memory (flat-buffer order q, k, v), else one GEMM per matrix.  (The bias gradients come out of the
+    attention backward, see _attention_bwd.)"""
     tq, tk, tv = go.target("wq"), go.target("wk"), go.target("wv")
     step = H * H * 4
     if tk.data_ptr() - tq.data_ptr() == step and tv.data_ptr() - tk.data_ptr() == step:
@@ -297,10 +302,6 @@ def _qkv_grads(go, dqkv, x_bf, H, M):
     else:
         for i, t in enumerate((tq, tk, tv)):
             _wgrad(dqkv[:, i * H:(i + 1) * H], x_bf, H, H, M, out=t, lda=3 * H)
-    for i, n in enumerate(("bq", "bk", "bv")):
-        t = go.target(n)
-        if t is not None:
-            L.colsum(dqkv[:, i * H:(i + 1) * H], t, M=M, N=H, ld=3 * H, accumulate=True)
 
 
 def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=False, dx_colsum=None):
@@ -340,7 +341,7 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
             L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), wo_t.data_ptr(), None, B, H, H)
         do = _bf16((M, H), dev)
         L.gemm(dx1_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
-        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, dc)
+        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, dc, go)
         _qkv_grads(go, dqkv, sv.h1, H, M)
         dh1 = _f32((M, H), dev)
         L.gemm(dqkv, sh.wqkv, dh1, M=M, N=H, K=3 * H, b_mn=True)
@@ -364,7 +365,7 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
             do2 = _bf16((M, H), dev)
             L.call("tavk_permute_bshd_bhds", do.data_ptr(), do2.data_ptr(), B, S, spec.heads, H // spec.heads, 1)
             do = do2
-        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, None)
+        dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, None, go)
         _qkv_grads(go, dqkv, sv.x_bf, H, M)
         dx = _f32((M, H), dev)
         L.gemm(dqkv, sh.wqkv, dx, M=M, N=H, K=3 * H, b_mn=True, resid=da)

@@ -140,8 +140,13 @@ def test_attention_fwd_bwd(L, B, S, nh, use_bias):
     # rank-1 dV term of the post-softmax mask quirk
     rowscale = torch.randn(B, S, generator=g).cuda()
     rank1 = torch.randn(B, H, generator=g).cuda()
+    db = [torch.full((H,), 0.25, device="cuda") for _ in range(3)]   # bias-gradient accumulators (+= semantics)
     L.attn_bwd(q, k, v, o, do, lse, delta, dqkv[..., :H], dqkv[..., H:2 * H], dqkv[..., 2 * H:], B=B, S=S, nh=nh,
-               ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H, key_bias=bias, dv_rowscale=rowscale, dv_rank1=rank1)
+               ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H, key_bias=bias, dv_rowscale=rowscale, dv_rank1=rank1,
+               dbq=db[0], dbk=db[1], dbv=db[2])
+    for i in range(3):   # column sums of dq / dk / dv over all B*S rows (fp32 sums of the values before bf16 rounding)
+        want = dqkv[..., i * H:(i + 1) * H].float().sum(dim=(0, 1))
+        assert (db[i] - 0.25 - want).abs().max().item() < 2e-2 * max(1.0, want.abs().max().item())
     unpack = lambda t: t.transpose(1, 2).reshape(B, S, H)  # noqa: E731
     if S == 1:  # softmax over one key is constant: dQ = dK = 0 exactly; only rounding noise may remain
         assert dqkv[..., :2 * H].float().abs().max().item() < 1e-6
