@@ -339,7 +339,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tma_load_3d(sQ, &tmap_q, q_full, h * kTcD, q0, b);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j % kF3Stages;
-                mbar_wait(&kv_empty[st], ((j / kF3Stages) & 1) ^ 1);
+                mbar_wait_backoff<128>(&kv_empty[st], ((j / kF3Stages) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * kF3KTile);
                 tma_load_3d(sK + st * kF3KTile, &tmap_k, &kv_full[st], h * kTcD, j * kF3KV, b);
                 tma_load_3d(sV + st * kF3KTile, &tmap_v, &kv_full[st], h * kTcD, j * kF3KV, b);
@@ -355,7 +355,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint64_t dp0 = umma_smem_desc(smem_u32(sP), 16, 1024);
         auto issue_qk = [&](int j) {
             const int st = j % kF3Stages;
-            mbar_wait(&kv_full[st], (j / kF3Stages) & 1);
+            mbar_wait_backoff<32>(&kv_full[st], (j / kF3Stages) & 1);
             tc_fence_after();
             if (leader) {
                 const uint64_t dk = dk0 + (uint64_t)(st * (kF3KTile >> 4));
@@ -371,7 +371,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         issue_qk(0);
         for (int j = 0; j < n_tiles; ++j) {
             if (j + 1 < n_tiles) issue_qk(j + 1);
-            mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+            mbar_wait_backoff<32>(&p_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             if (leader) {
                 const int st = j % kF3Stages;
@@ -402,18 +402,21 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tmem_ld_32x32(ts + 32, reinterpret_cast<uint32_t(&)[32]>(sr[32]));
             tmem_ld_wait();
             const int valid = p.S - j * kF3KV;   // key columns of this tile that exist
-            float mx = -INFINITY;
-            if (valid >= 64) {
+            if (valid < 64) {
 #pragma unroll
-                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
-            } else {
-#pragma unroll
-                for (int c = 0; c < 64; ++c) {
+                for (int c = 0; c < 64; ++c)
                     if (c >= valid) sr[c] = 0xff800000u;  // -inf
-                    mx = fmaxf(mx, __uint_as_float(sr[c]));
-                }
             }
-            mx *= p.scale_log2;
+            // four independent running maxima (a single 64-long dependent chain would cost ~250 cycles of latency)
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 64; c += 8) {
+                mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+            }
+            float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
             float factor = 1.0f;
             const bool grow = mx > m_used + kRescaleThreshold;   // always true on the first tile (m_used = -inf)
             if (grow) {
@@ -421,16 +424,18 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 l *= factor;
                 m_used = mx;
             }
-            float sum = 0.f;
+            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const float neg_m = -m_used;
 #pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
-                sum += p0 + p1;
-                sr[c >> 1] = pack_bf16x2(p0, p1);
+            for (int c = 0; c < 64; c += 8) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sr[c + i]), p.scale_log2, neg_m));
+                sum0 += e[0] + e[1]; sum1 += e[2] + e[3]; sum2 += e[4] + e[5]; sum3 += e[6] + e[7];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sr[(c >> 1) + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
             }
-            l += sum;
+            l += (sum0 + sum1) + (sum2 + sum3);
             // P[j&1] must no longer be read by PV(j-2)
             if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
             const uint32_t pbase = smem_u32(sP + (j & 1) * kF3PBytes) + row * 128;
@@ -933,7 +938,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         for (int i = 0; i < n_steps; ++i) {
             const int st = i % kB3Stages;
-            mbar_wait(&qdo_empty[st], ((i / kB3Stages) & 1) ^ 1);
+            mbar_wait_backoff<128>(&qdo_empty[st], ((i / kB3Stages) & 1) ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
                 tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
@@ -962,8 +967,8 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int i = 0; i <= n_steps; ++i) {
             if (i < n_steps) {
                 const int st = i % kB3Stages;
-                mbar_wait(&qdo_full[st], (i / kB3Stages) & 1);
-                if (i >= 1) mbar_wait(st_free, (i - 1) & 1);
+                mbar_wait_backoff<32>(&qdo_full[st], (i / kB3Stages) & 1);
+                if (i >= 1) mbar_wait_backoff<32>(st_free, (i - 1) & 1);
                 tc_fence_after();
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
@@ -978,7 +983,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
             if (i >= 1) {
                 const int kstep = i - 1, st = kstep % kB3Stages;
-                mbar_wait(pds_full, kstep & 1);
+                mbar_wait_backoff<32>(pds_full, kstep & 1);
                 tc_fence_after();
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
@@ -1124,7 +1129,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             tma_load_3d(sDO, &tmap_do, qdo_full, h * kTcD, q0, b);
             for (int j = 0; j < n_steps; ++j) {
                 const int st = j % kB3Stages;
-                mbar_wait(&kv_empty[st], ((j / kB3Stages) & 1) ^ 1);
+                mbar_wait_backoff<128>(&kv_empty[st], ((j / kB3Stages) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * kBwSmall);
                 tma_load_3d(sK + st * kBwSmall, &tmap_k, &kv_full[st], h * kTcD, j * kBwStep, b);
                 tma_load_3d(sV + st * kBwSmall, &tmap_v, &kv_full[st], h * kTcD, j * kBwStep, b);
@@ -1142,8 +1147,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         for (int j = 0; j <= n_steps; ++j) {
             if (j < n_steps) {
                 const int st = j % kB3Stages;
-                mbar_wait(&kv_full[st], (j / kB3Stages) & 1);
-                if (j >= 1) mbar_wait(s_free, (j - 1) & 1);
+                mbar_wait_backoff<32>(&kv_full[st], (j / kB3Stages) & 1);
+                if (j >= 1) mbar_wait_backoff<32>(s_free, (j - 1) & 1);
                 tc_fence_after();
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
@@ -1158,7 +1163,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             }
             if (j >= 1) {
                 const int kstep = j - 1, st = kstep % kB3Stages;
-                mbar_wait(ds_full, kstep & 1);
+                mbar_wait_backoff<32>(ds_full, kstep & 1);
                 tc_fence_after();
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
