@@ -374,8 +374,15 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
                 f.write("%8.3f %4d %8.4f %7.1f %s\n" % row)
     achieved = total_flops / (total_ms * 1e-3) / 1e12 if total_ms > 0 else 0.0
     peak = peaks["bf16_tflops"]
+    traffic, traffic_of = None, None
+    try:   # DRAM bytes per launch of the heaviest signature, from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_of = tj["traffic_bytes"], {k: tj[k] for k in ("signature", "algorithmic_bytes", "source")}
+    except Exception:  # noqa: BLE001
+        pass
     roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+            "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_of, "peak_source": peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
             "launches_per_step": sum(sigs.values()), "distinct_shapes": len(sigs), "flops_per_step": total_flops,
             "avg_launch_ms": total_ms / max(1, sum(sigs.values())), "share_of_step": total_ms / step_ms,
             "method": "each distinct GEMM signature of the step: 10 launches captured in a CUDA graph, replayed twice between CUDA events on the launching stream (same operands every launch: L2-warm for the small shapes)"}
