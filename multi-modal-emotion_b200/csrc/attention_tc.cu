@@ -34,6 +34,15 @@ constexpr uint32_t kTcTmemCols = 512;                // S[2] 256 + O 64 -> next 
 constexpr float kTcLog2e = 1.4426950408889634f, kTcLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
 
+// The two-CTA-per-SM kernels use every byte of their 113 KB share, so they cannot afford 1 KB of alignment slack: the
+// dynamic shared-memory window of a CTA starts 1024-byte aligned when the kernel has no static shared memory (checked).
+TAVK_DEVINL uint8_t* smem_base_1024(uint8_t* raw) {
+    if ((smem_u32(raw) & 1023u) != 0u) {
+        if (threadIdx.x == 0) printf("tavk: dynamic shared memory is not 1024-byte aligned (%u)\n", smem_u32(raw));
+        __trap();
+    }
+    return raw;
+}
 TAVK_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 TAVK_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -285,10 +294,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 //   S double-buffered in TMEM (2 x 64 columns) + O (64 columns); P double-buffered in smem (2 x 16 KB).
 // =====================================================================================================
 constexpr int kF3KV = 64;
-constexpr int kF3Stages = 3;
+constexpr int kF3Stages = 4;
 constexpr int kF3KTile = kF3KV * kTcD * 2;            // 8 KB (K or V tile)
 constexpr int kF3PBytes = kTcQ * kF3KV * 2;           // 16 KB
-constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 2 * kF3PBytes + 1024 + 256;   // 97.25 KB + slack
+constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 2 * kF3PBytes + 256;   // 112.25 KB: two CTAs per SM, no slack
 constexpr int kF3Threads = 6 * 32;
 constexpr uint32_t kF3TmemCols = 256;
 
@@ -297,7 +306,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_base_1024(smem_raw);
     uint8_t* sQ = smem;
     uint8_t* sK = smem + kTcTile;
     uint8_t* sV = sK + kF3Stages * kF3KTile;
@@ -881,8 +890,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // =====================================================================================================
 constexpr int kB3Stages = 2;
 constexpr int kB3Threads = 6 * 32;
+// dK/dV kernel: two ring stages.  A third stage (with a single statistics buffer to stay under 113 KB) was measured
+// slower (346 vs 332 us at B=16 S=1464): unlike the dQ kernel its pace is not set by the TMA look-ahead.
 constexpr int kDkv3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + 2 * kBwPBytes + kB3Stages * 128 * 4 + 1024 + 256;
-constexpr int kDq3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + kBwPBytes + 1024 + 256;
+constexpr int kDq3Stages = 4;             // K_j/V_j ring of the dQ kernel: three steps of TMA look-ahead (2 stages: 258 us,
+                                          // 3 stages: 208 us at B=16 S=1464 — the ring depth, not the math, set the pace)
+constexpr int kDq3Smem = 2 * kTcTile + kDq3Stages * 2 * kBwSmall + kBwPBytes + 256;
 
 __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -1086,17 +1099,17 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                        const AttnTcBwdDev p) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_base_1024(smem_raw);
     uint8_t* sQ = smem;
     uint8_t* sDO = smem + kTcTile;
     uint8_t* sK = sDO + kTcTile;                      // ring
-    uint8_t* sV = sK + kB3Stages * kBwSmall;          // ring
-    uint8_t* sDS = sV + kB3Stages * kBwSmall;
+    uint8_t* sV = sK + kDq3Stages * kBwSmall;          // ring
+    uint8_t* sDS = sV + kDq3Stages * kBwSmall;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + kBwPBytes);
     uint64_t* qdo_full = bars;
     uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + kB3Stages;
-    uint64_t* s_full = kv_empty + kB3Stages;
+    uint64_t* kv_empty = kv_full + kDq3Stages;
+    uint64_t* s_full = kv_empty + kDq3Stages;
     uint64_t* s_free = s_full + 1;
     uint64_t* ds_full = s_free + 1;
     uint64_t* ds_empty = ds_full + 1;
@@ -1110,7 +1123,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
         mbar_init(qdo_full, 1);
-        for (int i = 0; i < kB3Stages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < kDq3Stages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(ds_full, 4); mbar_init(ds_empty, 1);
         mbar_init(done, 1);
         mbar_fence_init();
@@ -1128,8 +1141,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             tma_load_3d(sQ, &tmap_q, qdo_full, h * kTcD, q0, b);
             tma_load_3d(sDO, &tmap_do, qdo_full, h * kTcD, q0, b);
             for (int j = 0; j < n_steps; ++j) {
-                const int st = j % kB3Stages;
-                mbar_wait_backoff<128>(&kv_empty[st], ((j / kB3Stages) & 1) ^ 1);
+                const int st = j % kDq3Stages;
+                mbar_wait_backoff<128>(&kv_empty[st], ((j / kDq3Stages) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * kBwSmall);
                 tma_load_3d(sK + st * kBwSmall, &tmap_k, &kv_full[st], h * kTcD, j * kBwStep, b);
                 tma_load_3d(sV + st * kBwSmall, &tmap_v, &kv_full[st], h * kTcD, j * kBwStep, b);
@@ -1146,8 +1159,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc_fence_after();
         for (int j = 0; j <= n_steps; ++j) {
             if (j < n_steps) {
-                const int st = j % kB3Stages;
-                mbar_wait_backoff<32>(&kv_full[st], (j / kB3Stages) & 1);
+                const int st = j % kDq3Stages;
+                mbar_wait_backoff<32>(&kv_full[st], (j / kDq3Stages) & 1);
                 if (j >= 1) mbar_wait_backoff<32>(s_free, (j - 1) & 1);
                 tc_fence_after();
                 if (leader) {
@@ -1162,7 +1175,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 __syncwarp();
             }
             if (j >= 1) {
-                const int kstep = j - 1, st = kstep % kB3Stages;
+                const int kstep = j - 1, st = kstep % kDq3Stages;
                 mbar_wait_backoff<32>(ds_full, kstep & 1);
                 tc_fence_after();
                 if (leader) {
