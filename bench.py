@@ -179,7 +179,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # Optional (TAVK_COMM_SMS=n): give NCCL a fixed CTA budget and keep as many SMs out of the persistent GEMM's grid
+        # (tavk_reserve_sms).  Off by default: measured at 2 GPUs it costs more than it hides (649 vs 676 samples/s, n=8).
+        comm_sms = int(os.environ.get("TAVK_COMM_SMS", "0"))
+        if comm_sms > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
+            os.environ.setdefault("NCCL_MIN_CTAS", str(min(4, comm_sms)))
         dist.init_process_group("nccl", device_id=dev)
+        if comm_sms > 0:
+            L.reserve_sms(comm_sms)
     L.require_device()   # fails loudly when the CUDA extension / an sm_100 device is missing: no fallback
 
     peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}

@@ -47,6 +47,9 @@ int tavk_version(void);
 /* 0 when an sm_100 device is current and usable, 3 otherwise (message in tavk_last_error). */
 int tavk_device_check(void);
 int tavk_sm_count(void);
+/* The persistent GEMM uses at most tavk_sm_count() - n SMs from now on (process-wide; 0 restores the default).  Data-
+ * parallel hosts reserve a few SMs for the NCCL all-reduce kernels that run concurrently with backward. */
+int tavk_reserve_sms(int n);
 
 /* ------------------------------------------------------------------------------------------------------------
  * tavk_gemm_bf16 — C[M,N] = epi(alpha * sum_k A[m,k] * B[n,k]); bf16 operands, fp32 accumulate (tcgen05/TMEM, TMA).

@@ -71,6 +71,7 @@ SIGNATURES = {
     "tavk_version": [],
     "tavk_device_check": [],
     "tavk_sm_count": [],
+    "tavk_reserve_sms": [_I],
     "tavk_gemm_bf16": [C.POINTER(GemmArgs), _P],
     "tavk_attn_fwd": [C.POINTER(AttnArgs), _P],
     "tavk_attn_bwd": [C.POINTER(AttnBwdArgs), _P],
@@ -148,6 +149,11 @@ def call(name, *args):
     rc = getattr(lib(), name)(*args, torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         _check(rc, name)
+
+
+def reserve_sms(n):
+    """Keep n SMs out of the persistent GEMM's grid (for concurrently running NCCL kernels)."""
+    _check(lib().tavk_reserve_sms(int(n)), "tavk_reserve_sms")
 
 
 def require_device():

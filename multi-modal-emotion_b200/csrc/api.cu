@@ -31,6 +31,15 @@ int sm_count() {
     return cached[dev];
 }
 
+// SMs the persistent GEMM leaves to other work.  Data-parallel runs reserve a few for the NCCL all-reduce kernels: a
+// persistent one-CTA-per-SM GEMM otherwise owns every SM, NCCL's CTAs only get in at kernel boundaries, and the
+// GEMM CTAs they displace start late — with a static tile schedule the whole kernel then waits for them.
+static int g_reserved_sms = 0;
+int gemm_sm_budget() {
+    const int n = sm_count() - g_reserved_sms;
+    return n < 1 ? 1 : n;
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -50,6 +59,15 @@ extern "C" const char* tavk_last_error(void) { return tavk::g_err; }
 extern "C" int tavk_version(void) { return TAVK_VERSION; }
 
 extern "C" int tavk_sm_count(void) { return tavk::sm_count(); }
+
+extern "C" int tavk_reserve_sms(int n) {
+    if (n < 0 || n >= tavk::sm_count()) {
+        tavk::set_error("tavk_reserve_sms: %d is outside [0, %d)", n, tavk::sm_count());
+        return 1;
+    }
+    tavk::g_reserved_sms = n;
+    return 0;
+}
 
 extern "C" int tavk_device_check(void) {
     int dev = 0;

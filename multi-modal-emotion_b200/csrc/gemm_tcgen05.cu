@@ -500,7 +500,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
                "tavk_gemm_bf16: a_kstep needs a K-major A operand and a multiple of 8 elements");
 
     // tile-shape heuristic: the widest tile whose wave quantisation is not noticeably worse than a narrower one's
-    const int sms = sm_count();
+    const int sms = gemm_sm_budget();
     const int mblocks = (a->M + kBlockM - 1) / kBlockM;
     auto waves_eff = [&](int bn) {
         const long long tiles = (long long)groups * mblocks * ((a->N + bn - 1) / bn) * k_splits;
