@@ -1,22 +1,19 @@
-// tcgen05 / TMEM flash attention for head_dim 64 (v2 of the attention path; attention.cu keeps the mma.sync v1 that
-// still serves key-bias masks and very short sequences).
+// tcgen05 / TMEM flash attention for head_dim 64, forward and backward (attention.cu keeps the mma.sync v1 that still
+// serves key-bias masks and sequences shorter than 128).
 //
 // Replaces the same reference op sites as attention.cu: utils/TAVFormer.py:357-387 (QK^T/8, softmax, PV) and the HF
 // encoders' attention.  Motivation (profiles/r1_*): at the VideoMAE shape (S=1464, 192 (b,h) pairs) the mma.sync
 // kernels were 24 ms of a 90 ms step; the legacy tensor path peaks at a quarter of tcgen05's rate.
 //
-// Forward, one CTA = 128 queries of one (batch, head):
-//   warp 0      TMA producer: Q once, then a 3-stage ring of (K_j, V_j) 128x64 bf16 tiles (3-D tensor maps over
-//               [B][S][row], SWIZZLE_128B, rows >= S zero-filled by the hardware)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer:
-//                 S_j = Q K_j^T   (UMMA 128x128x16 x4, both operands K-major)        -> TMEM S[j&1] (128 fp32 columns)
-//                 O  += P_j V_j   (UMMA 128x64x16 x8, A = P from smem, B = V MN-major) -> TMEM O (64 columns)
-//               QK of tile j+1 is issued before PV of tile j, so the tensor pipe works while tile j's softmax runs
-//   warps 2..5  softmax: one thread per query row (TMEM lane).  tcgen05.ld the 128 scores of the row, row max / sum
-//               without any shuffle, p = ex2(s*scale*log2e - m), bf16 P written to smem in the UMMA K-major SW128
-//               layout.  Lazy rescaling: the running max only moves (and O in TMEM is only rescaled, tcgen05.ld/st)
-//               when it grows by more than 8 in the log2 domain, so the common path never touches O.
-// Epilogue: O / l -> bf16 rows, lse = (m + log2 l) ln2.
+// Common shape of the three kernels: one CTA = 128 rows (queries, or keys for dK/dV) of one (batch, head); 192 threads:
+//   warp 0      TMA producer (3-D tensor maps over [B][S][row], SWIZZLE_128B, rows >= S zero-filled by the hardware)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulators S / dP / O / dQ / dK / dV in TMEM)
+//   warps 2..5  elementwise: one thread per tile row (TMEM lane), tcgen05.ld -> ex2 / dS in registers -> bf16 P / dS
+//               staged in shared memory in the UMMA K-major SW128 layout for the next MMA
+// Every kernel keeps within 113 KB of shared memory and 256 TMEM columns so that TWO CTAs share an SM: with d = 64 the
+// elementwise stage, not the tensor pipe, sets the pace (16 ex2/clk/SM against 8192 tensor FLOP/clk/SM), and two
+// independent CTAs keep each other's idle phases busy.  An earlier one-CTA-per-SM version (8 elementwise warps, 128-key
+// tiles, 2 threads per row) measured 286 / 386 / 294 us (fwd / dK,dV / dQ) at B=16, S=1464; these: 191 / 332 / 207 us.
 #include "../../include/tavk.h"
 #include <stdlib.h>
 
@@ -25,12 +22,7 @@
 namespace tavk {
 
 constexpr int kTcQ = 128, kTcKV = 128, kTcD = 64;
-constexpr int kTcStages = 3;
 constexpr int kTcTile = kTcKV * kTcD * 2;            // 16 KB  (K, V, Q tiles)
-constexpr int kTcPBytes = kTcQ * kTcKV * 2;          // 32 KB  (P tile, two 64-key SW128 atoms)
-constexpr int kTcSmem = kTcTile * (1 + 2 * kTcStages) + 2 * kTcPBytes + 6 * 128 * 4 + 1024 + 256;
-constexpr int kTcThreads = 10 * 32;   // producer, MMA issuer, 8 softmax warps (2 per TMEM lane quarter)
-constexpr uint32_t kTcTmemCols = 512;                // S[2] 256 + O 64 -> next power of two
 constexpr float kTcLog2e = 1.4426950408889634f, kTcLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;
 
@@ -73,225 +65,12 @@ struct AttnTcDev {
     float scale_log2;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
-    pdl_wait();   // programmatic dependent launch: see common.cuh
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + kTcTile;
-    uint8_t* sV = sK + kTcStages * kTcTile;
-    uint8_t* sP = sV + kTcStages * kTcTile;
-    float* s_part = reinterpret_cast<float*>(sP + 2 * kTcPBytes);   // [2 tiles parity][2 halves][128] row max, [2][128] row sum
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 6 * 128);
-    uint64_t* q_full = bars;               // 1
-    uint64_t* kv_full = bars + 1;          // kTcStages
-    uint64_t* kv_empty = kv_full + kTcStages;
-    uint64_t* s_full = kv_empty + kTcStages;  // 2
-    uint64_t* p_full = s_full + 2;            // 2
-    uint64_t* p_empty = p_full + 2;           // 2
-    uint64_t* pv_done = p_empty + 2;          // 1
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
-
-    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
-    const int q0 = blockIdx.x * kTcQ, h = blockIdx.y, b = blockIdx.z;
-    const int n_tiles = (p.S + kTcKV - 1) / kTcKV;
-
-    if (warp_idx == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_k);
-        tma_prefetch_desc(&tmap_v);
-        mbar_init(q_full, 1);
-        for (int i = 0; i < kTcStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1); }
-        mbar_init(pv_done, 1);
-        mbar_fence_init();
-    }
-    if (warp_idx == 1) tmem_alloc<kTcTmemCols>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
-    const uint32_t tmem_o = tmem_base + 256;
-
-    if (warp_idx == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, kTcTile);
-            tma_load_3d(sQ, &tmap_q, q_full, h * kTcD, q0, b);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j % kTcStages;
-                const uint32_t ph = (j / kTcStages) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * kTcTile);
-                tma_load_3d(sK + st * kTcTile, &tmap_k, &kv_full[st], h * kTcD, j * kTcKV, b);
-                tma_load_3d(sV + st * kTcTile, &tmap_v, &kv_full[st], h * kTcD, j * kTcKV, b);
-            }
-        }
-    } else if (warp_idx == 1) {
-        // whole warp runs the loop (warp-uniform control flow and operands), one elected lane issues
-        const bool leader = elect_one();
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(kTcQ, kTcKV, false, false);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(kTcQ, kTcD, false, true);
-        const uint64_t dq0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
-        const uint64_t dk0 = umma_smem_desc(smem_u32(sK), 16, 1024);
-        const uint64_t dv0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
-        const uint64_t dp0 = umma_smem_desc(smem_u32(sP), 16, 1024);
-        auto issue_qk = [&](int j) {
-            const int st = j % kTcStages;
-            mbar_wait(&kv_full[st], (j / kTcStages) & 1);
-            tc_fence_after();
-            if (leader) {
-                const uint64_t dk = dk0 + (uint64_t)(st * (kTcTile >> 4));
-                const uint32_t tmem_s = tmem_base + (j & 1) * kTcKV;
-#pragma unroll
-                for (int k = 0; k < kTcD / 16; ++k) umma_bf16(tmem_s, dq0 + 2 * k, dk + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                umma_commit(&s_full[j & 1]);
-            }
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0);
-        tc_fence_after();
-        issue_qk(0);
-        for (int j = 0; j < n_tiles; ++j) {
-            if (j + 1 < n_tiles) issue_qk(j + 1);
-            mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            if (leader) {
-                const int st = j % kTcStages;
-                const uint64_t dp = dp0 + (uint64_t)((j & 1) * (kTcPBytes >> 4));
-                const uint64_t dv = dv0 + (uint64_t)(st * (kTcTile >> 4));
-#pragma unroll
-                for (int k = 0; k < kTcKV / 16; ++k)
-                    umma_bf16(tmem_o, dp + (uint64_t)((k >> 2) * ((kTcQ * 128) >> 4) + (k & 3) * 2), dv + (uint64_t)(k * (2048 >> 4)),
-                              idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&kv_empty[st]);
-                umma_commit(&p_empty[j & 1]);
-                umma_commit(pv_done);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===================== softmax / epilogue: two threads per query row (TMEM lane), 64 key columns each ========
-        const int quarter = warp_idx & 3, half = (warp_idx - 2) >> 2;
-        const int row = quarter * 32 + lane;
-        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        const uint32_t pair_bar = 1 + quarter;          // named barrier shared by the two warps of this lane quarter
-        float m_used = -INFINITY, l = 0.f;
-        for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            uint32_t sr[64];
-            const uint32_t ts = tmem_base + lane_sel + (uint32_t)((j & 1) * kTcKV + half * 64);
-            tmem_ld_32x32(ts + 0, reinterpret_cast<uint32_t(&)[32]>(sr[0]));
-            tmem_ld_32x32(ts + 32, reinterpret_cast<uint32_t(&)[32]>(sr[32]));
-            tmem_ld_wait();
-            const int valid = p.S - (j * kTcKV + half * 64);   // key columns of this thread's slab that exist
-            float mx = -INFINITY;
-            if (valid >= 64) {
-#pragma unroll
-                for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
-            } else {
-#pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    if (c >= valid) sr[c] = 0xff800000u;  // -inf
-                    mx = fmaxf(mx, __uint_as_float(sr[c]));
-                }
-            }
-            // combine the two half-row maxima (double-buffered by tile parity: one named barrier per tile suffices)
-            float* mp = s_part + (j & 1) * 256;
-            mp[half * 128 + row] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            mx = fmaxf(mp[row], mp[128 + row]) * p.scale_log2;
-            float factor = 1.0f;
-            const bool grow = mx > m_used + kRescaleThreshold;   // always true on the first tile (m_used = -inf)
-            if (grow) {
-                factor = ex2_approx(m_used - mx);                 // 0 on the first tile
-                l *= factor;
-                m_used = mx;
-            }
-            float sum = 0.f;
-            const float neg_m = -m_used;
-#pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
-                sum += p0 + p1;
-                sr[c >> 1] = pack_bf16x2(p0, p1);
-            }
-            l += sum;
-            // P[j&1] must no longer be read by PV(j-2)
-            if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
-            const uint32_t pbase = smem_u32(sP + (j & 1) * kTcPBytes) + half * (kTcQ * 128) + row * 128;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
-                             "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
-                             : "memory");
-            }
-            // rare: the running max moved -> rescale this warp's 32 rows x 32 columns of O (needs PV(j-1) retired)
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
-                mbar_wait(pv_done, (j - 1) & 1);
-                tc_fence_after();
-                uint32_t orow[32];
-                const uint32_t to = tmem_o + lane_sel + half * 32;
-                tmem_ld_32x32(to, orow);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
-                tmem_st_32x32(to, orow);
-                tmem_st_wait();
-            }
-            fence_proxy_async_smem();   // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[j & 1]);
-        }
-        // ---- epilogue: total row sum = sum of the two halves; each thread normalises and stores 32 of the 64 columns
-        float* lp = s_part + 512;
-        lp[half * 128 + row] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        l = lp[row] + lp[128 + row];
-        // pv_done completes one phase per PV(j); a parity wait only tells "odd or even number of completions", and this
-        // warp is only known to be past PV(n-3) (the P-buffer hand-off): wait for PV(n-2) first, then for PV(n-1)
-        if (n_tiles >= 2) mbar_wait(pv_done, (n_tiles - 2) & 1);
-        mbar_wait(pv_done, (n_tiles - 1) & 1);
-        tc_fence_after();
-        const int qrow = q0 + row;
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint32_t orow[32];
-        tmem_ld_32x32(tmem_o + lane_sel + half * 32, orow);
-        tmem_ld_wait();
-        if (qrow < p.S) {
-            float v[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(orow[c]) * inv;
-            __nv_bfloat16* dst = p.o + ((long long)b * p.S + qrow) * p.ld_o + h * kTcD + half * 32;
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                d4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-            if (p.lse && half == 0) p.lse[((long long)b * p.nh + h) * p.S + qrow] = l > 0.f ? (m_used + log2f(l)) * kTcLn2 : -INFINITY;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp_idx == 1) {
-        tc_fence_after();
-        tmem_dealloc<kTcTmemCols>(tmem_base);
-    }
-}
-
 // =====================================================================================================
-// Forward, v3: the same pipeline cut to HALF the footprint so that TWO CTAs share an SM (192 threads, 97 KB of shared
-// memory, 256 TMEM columns each).  With head_dim 64 the kernel is bound by the softmax (16 exp/clk/SM against 8192
-// tensor FLOP/clk/SM: a 128x128 score tile costs 1024 MUFU cycles but only 512 tensor cycles), so what matters is that
-// the MUFU pipe never idles: two independent CTAs per SM are in different phases (one in row-max / packing / barrier
-// hand-offs while the other streams ex2), which the single-CTA version above could not do with 2 warps per scheduler.
-//   KV tile = 64 keys; one softmax THREAD per query row (4 warps): no cross-warp max/sum exchange, no named barriers.
-//   S double-buffered in TMEM (2 x 64 columns) + O (64 columns); P double-buffered in smem (2 x 16 KB).
+// Forward.  KV tile = 64 keys, 4-stage (K_j, V_j) ring; S double-buffered in TMEM (2 x 64 columns) + O (64 columns); P
+// double-buffered in smem (2 x 16 KB).  QK of tile j+1 is issued before PV of tile j, so the tensor pipe works while
+// tile j's softmax runs.  Online softmax without any shuffle (thread = row); lazy rescaling: the running max only moves
+// (and O in TMEM is only rescaled, tcgen05.ld/st) when it grows by more than 8 in the log2 domain.
+// Epilogue: O / l -> bf16 rows, lse = (m + log2 l) ln2.
 // =====================================================================================================
 constexpr int kF3KV = 64;
 constexpr int kF3Stages = 4;
@@ -508,22 +287,19 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // =====================================================================================================
-// Backward (mask-free mode), two tcgen05 kernels that recompute P from the saved log-sum-exp:
+// Backward (mask-free mode), two kernels that recompute P from the saved log-sum-exp:
 //   dK/dV kernel: CTA = 128 keys of one (b,h); loops over 64-query steps.
-//       S^T = K Q_i^T, dP^T = V dO_i^T               (UMMA 128x64x16 x4 each -> TMEM, double-buffered)
-//       P^T = ex2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)   (8 warps, thread = key row x 32 query columns)
+//       S^T = K Q_i^T, dP^T = V dO_i^T               (UMMA 128x64x16 x4 each -> TMEM)
+//       P^T = ex2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)   (thread = key row, two 32-query halves)
 //       dV += P^T dO_i, dK += dS^T Q_i               (A = bf16 P^T / dS^T from smem, B = dO_i / Q_i MN-major)
 //   dQ kernel:    CTA = 128 queries; loops over 64-key steps.
 //       S = Q K_j^T, dP = dO V_j^T -> dS = ex2(S c - lse_row)(dP - delta_row) -> dQ += dS K_j
-// No atomics, deterministic.  Queries >= S are neutralised with lse = +inf (P = 0), keys >= S by zeroing P.
+// No atomics in the data path, deterministic.  Queries >= S are neutralised with lse = +inf (P = 0), keys >= S by
+// zeroing P.  Optional: the q/k/v projection bias gradients (column sums of dQ / dK / dV) from the epilogues.
 // =====================================================================================================
 constexpr int kBwStep = 64;                              // inner-loop tile (queries for dK/dV, keys for dQ)
-constexpr int kBwStages = 4;
 constexpr int kBwSmall = kBwStep * kTcD * 2;             // 8 KB
-constexpr int kBwThreads = 10 * 32;                      // producer, MMA, 8 elementwise warps
 constexpr int kBwPBytes = 128 * kBwStep * 2;             // 16 KB: [128 rows][64 k] bf16, one SW128 atom column
-constexpr int kDkvSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 4 * kBwPBytes + kBwStages * 128 * 4 + 1024 + 256;
-constexpr int kDqSmem = 2 * kTcTile + kBwStages * 2 * kBwSmall + 2 * kBwPBytes + 1024 + 256;
 
 struct AttnTcBwdDev {
     const float *lse, *delta;
@@ -546,348 +322,8 @@ TAVK_DEVINL void st_row_chunks(uint32_t tile_base, int row, int half, const uint
     }
 }
 
-__global__ void __launch_bounds__(kBwThreads, 1)
-attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                       const AttnTcBwdDev p) {
-    pdl_wait();   // programmatic dependent launch: see common.cuh
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;
-    uint8_t* sV = smem + kTcTile;
-    uint8_t* sQ = sV + kTcTile;                       // ring: [stage] Q_i
-    uint8_t* sDO = sQ + kBwStages * kBwSmall;         // ring: [stage] dO_i
-    uint8_t* sP = sDO + kBwStages * kBwSmall;         // [2] P^T
-    uint8_t* sDS = sP + 2 * kBwPBytes;                // [2] dS^T
-    float* s_stats = reinterpret_cast<float*>(sDS + 2 * kBwPBytes);   // ring: [stage][64 lse*log2e | 64 delta]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + kBwStages * 128);
-    uint64_t* kv_full = bars;
-    uint64_t* qdo_full = bars + 1;
-    uint64_t* qdo_empty = qdo_full + kBwStages;
-    uint64_t* st_full = qdo_empty + kBwStages;   // 2
-    uint64_t* pds_full = st_full + 2;            // 2
-    uint64_t* pds_empty = pds_full + 2;          // 2
-    uint64_t* done = pds_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
-
-    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
-
-    if (warp_idx == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
-        mbar_init(kv_full, 1);
-        for (int i = 0; i < kBwStages; ++i) { mbar_init(&qdo_full[i], 2); mbar_init(&qdo_empty[i], 1); }  // TMA + stats
-        for (int i = 0; i < 2; ++i) { mbar_init(&st_full[i], 1); mbar_init(&pds_full[i], 8); mbar_init(&pds_empty[i], 1); }
-        mbar_init(done, 1);
-        mbar_fence_init();
-    }
-    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
-    const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320;
-
-    if (warp_idx == 0) {
-        // producer: lane 0 drives TMA; all lanes stage the per-query statistics of the step (lse*log2e, delta)
-        const long long stat_off = ((long long)b * p.nh + h) * p.S;
-        if (lane == 0) {
-            mbar_arrive_expect_tx(kv_full, 2 * kTcTile);
-            tma_load_3d(sK, &tmap_k, kv_full, h * kTcD, k0, b);
-            tma_load_3d(sV, &tmap_v, kv_full, h * kTcD, k0, b);
-        }
-        for (int i = 0; i < n_steps; ++i) {
-            const int st = i % kBwStages;
-            mbar_wait(&qdo_empty[st], ((i / kBwStages) & 1) ^ 1);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
-                tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
-                tma_load_3d(sDO + st * kBwSmall, &tmap_do, &qdo_full[st], h * kTcD, i * kBwStep, b);
-            }
-#pragma unroll
-            for (int t = lane; t < kBwStep; t += 32) {
-                const int qi = i * kBwStep + t;
-                const bool ok = qi < p.S;
-                s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
-                s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qdo_full[st]);
-        }
-    } else if (warp_idx == 1) {
-        const bool leader = elect_one();
-        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S^T, dP^T
-        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dV, dK (B MN-major)
-        const uint64_t dK = umma_smem_desc(smem_u32(sK), 16, 1024), dV = umma_smem_desc(smem_u32(sV), 16, 1024);
-        const uint64_t dQk0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dDOk0 = umma_smem_desc(smem_u32(sDO), 16, 1024);
-        const uint64_t dQm0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dDOm0 = umma_smem_desc(smem_u32(sDO), 8192, 1024);
-        const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 16, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
-        mbar_wait(kv_full, 0);
-        tc_fence_after();
-        for (int i = 0; i <= n_steps; ++i) {
-            if (i < n_steps) {
-                const int st = i % kBwStages;
-                mbar_wait(&qdo_full[st], (i / kBwStages) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
-                    const uint32_t t_st = tmem_base + (i & 1) * 128, t_dp = t_st + 64;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-                    umma_commit(&st_full[i & 1]);
-                }
-                __syncwarp();
-            }
-            if (i >= 1) {
-                const int kstep = i - 1, st = kstep % kBwStages;
-                mbar_wait(&pds_full[kstep & 1], (kstep >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4)), po = (uint64_t)((kstep & 1) * (kBwPBytes >> 4));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dv, dP0 + po + 2 * k, dDOm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dk, dDS0 + po + 2 * k, dQm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&qdo_empty[st]);
-                    umma_commit(&pds_empty[kstep & 1]);
-                }
-                __syncwarp();
-            }
-        }
-        if (leader) umma_commit(done);
-        __syncwarp();
-    } else {
-        const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
-        const int row = quarter * 32 + lane;                       // key row inside the tile
-        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        for (int i = 0; i < n_steps; ++i) {
-            // per-column statistics of this thread's 32 queries, staged in smem by the producer (broadcast LDS.128)
-            const int stg = i % kBwStages;
-            mbar_wait(&qdo_full[stg], (i / kBwStages) & 1);
-            float lse2[32], dlt[32];
-            const float4* st4 = reinterpret_cast<const float4*>(s_stats + stg * 128 + half * 32);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 a = st4[c], d4 = st4[16 + c];
-                lse2[4 * c] = a.x; lse2[4 * c + 1] = a.y; lse2[4 * c + 2] = a.z; lse2[4 * c + 3] = a.w;
-                dlt[4 * c] = d4.x; dlt[4 * c + 1] = d4.y; dlt[4 * c + 2] = d4.z; dlt[4 * c + 3] = d4.w;
-            }
-            mbar_wait(&st_full[i & 1], (i >> 1) & 1);
-            tc_fence_after();
-            uint32_t s[32], dp[32];
-            const uint32_t t_st = tmem_base + lane_sel + (uint32_t)((i & 1) * 128 + half * 32);
-            tmem_ld_32x32(t_st, s);
-            tmem_ld_32x32(t_st + 64, dp);
-            tmem_ld_wait();
-            uint32_t pk[16], dsk[16];
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2[c]));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2[c + 1]));
-                pk[c >> 1] = pack_bf16x2(p0, p1);
-                dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt[c]), p1 * (__uint_as_float(dp[c + 1]) - dlt[c + 1]));
-            }
-            if (i >= 2) mbar_wait(&pds_empty[i & 1], ((i >> 1) - 1) & 1);
-            st_row_chunks(smem_u32(sP + (i & 1) * kBwPBytes), row, half, pk);
-            st_row_chunks(smem_u32(sDS + (i & 1) * kBwPBytes), row, half, dsk);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&pds_full[i & 1]);
-        }
-        mbar_wait(done, 0);
-        tc_fence_after();
-        const int key = k0 + row;
-        uint32_t r[32];
-        float v[32];
-        // dK
-        tmem_ld_32x32(tmem_dk + lane_sel + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
-        const long long out_off = ((long long)b * p.S + key) * p.ld_dqkv + h * kTcD + half * 32;
-        if (key < p.S) store_row32_bf16(p.dk + out_off, v);
-        // dV (+ rank-1 term of the post-softmax mask: dV[b,k,h,:] += m[b,k] * dc[b,h,:])
-        tmem_ld_32x32(tmem_dv + lane_sel + half * 32, r);
-        tmem_ld_wait();
-        float w = 0.f;
-        const float* dc = nullptr;
-        if (p.dv_rowscale != nullptr && key < p.S) {
-            w = p.dv_rowscale[(long long)b * p.S + key];
-            dc = p.dv_rank1 + ((long long)b * p.nh + h) * kTcD + half * 32;
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) + (dc ? w * __ldg(dc + c) : 0.f);
-        if (key < p.S) store_row32_bf16(p.dv + out_off, v);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp_idx == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
-__global__ void __launch_bounds__(kBwThreads, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                      const AttnTcBwdDev p) {
-    pdl_wait();   // programmatic dependent launch: see common.cuh
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sDO = smem + kTcTile;
-    uint8_t* sK = sDO + kTcTile;                      // ring
-    uint8_t* sV = sK + kBwStages * kBwSmall;          // ring
-    uint8_t* sDS = sV + kBwStages * kBwSmall;         // [2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kBwPBytes);
-    uint64_t* qdo_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + kBwStages;
-    uint64_t* s_full = kv_empty + kBwStages;     // 2
-    uint64_t* ds_full = s_full + 2;              // 2
-    uint64_t* ds_empty = ds_full + 2;            // 2
-    uint64_t* done = ds_empty + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
-
-    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int n_steps = (p.S + kBwStep - 1) / kBwStep;
-
-    if (warp_idx == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
-        mbar_init(qdo_full, 1);
-        for (int i = 0; i < kBwStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1); }
-        mbar_init(done, 1);
-        mbar_fence_init();
-    }
-    if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
-    const uint32_t tmem_dq = tmem_base + 256;
-
-    if (warp_idx == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(qdo_full, 2 * kTcTile);
-            tma_load_3d(sQ, &tmap_q, qdo_full, h * kTcD, q0, b);
-            tma_load_3d(sDO, &tmap_do, qdo_full, h * kTcD, q0, b);
-            for (int j = 0; j < n_steps; ++j) {
-                const int st = j % kBwStages;
-                mbar_wait(&kv_empty[st], ((j / kBwStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * kBwSmall);
-                tma_load_3d(sK + st * kBwSmall, &tmap_k, &kv_full[st], h * kTcD, j * kBwStep, b);
-                tma_load_3d(sV + st * kBwSmall, &tmap_v, &kv_full[st], h * kTcD, j * kBwStep, b);
-            }
-        }
-    } else if (warp_idx == 1) {
-        const bool leader = elect_one();
-        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, kBwStep, false, false);  // S, dP
-        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
-        const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dDO = umma_smem_desc(smem_u32(sDO), 16, 1024);
-        const uint64_t dKk0 = umma_smem_desc(smem_u32(sK), 16, 1024), dVk0 = umma_smem_desc(smem_u32(sV), 16, 1024);
-        const uint64_t dKm0 = umma_smem_desc(smem_u32(sK), 8192, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
-        mbar_wait(qdo_full, 0);
-        tc_fence_after();
-        for (int j = 0; j <= n_steps; ++j) {
-            if (j < n_steps) {
-                const int st = j % kBwStages;
-                mbar_wait(&kv_full[st], (j / kBwStages) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
-                    const uint32_t t_s = tmem_base + (j & 1) * 128, t_dp = t_s + 64;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_s, dQ + 2 * k, dKk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dDO + 2 * k, dVk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-                    umma_commit(&s_full[j & 1]);
-                }
-                __syncwarp();
-            }
-            if (j >= 1) {
-                const int kstep = j - 1, st = kstep % kBwStages;
-                mbar_wait(&ds_full[kstep & 1], (kstep >> 1) & 1);
-                tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4)), po = (uint64_t)((kstep & 1) * (kBwPBytes >> 4));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dq, dDS0 + po + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&kv_empty[st]);
-                    umma_commit(&ds_empty[kstep & 1]);
-                }
-                __syncwarp();
-            }
-        }
-        if (leader) umma_commit(done);
-        __syncwarp();
-    } else {
-        const int ew = warp_idx - 2, quarter = warp_idx & 3, half = ew >> 2;
-        const int row = quarter * 32 + lane;                       // query row inside the tile
-        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        const int qrow = q0 + row;
-        const long long stat_off = ((long long)b * p.nh + h) * p.S;
-        const float lse2 = qrow < p.S ? p.lse[stat_off + qrow] * kTcLog2e : INFINITY;
-        const float dlt = qrow < p.S ? p.delta[stat_off + qrow] : 0.f;
-        for (int j = 0; j < n_steps; ++j) {
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            uint32_t s[32], dp[32];
-            const uint32_t t_s = tmem_base + lane_sel + (uint32_t)((j & 1) * 128 + half * 32);
-            tmem_ld_32x32(t_s, s);
-            tmem_ld_32x32(t_s + 64, dp);
-            tmem_ld_wait();
-            const int valid = p.S - (j * kBwStep + half * 32);     // key columns of this thread's slab that exist
-            uint32_t dsk[16];
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2));
-                float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -lse2));
-                if (c >= valid) p0 = 0.f;
-                if (c + 1 >= valid) p1 = 0.f;
-                dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - dlt), p1 * (__uint_as_float(dp[c + 1]) - dlt));
-            }
-            if (j >= 2) mbar_wait(&ds_empty[j & 1], ((j >> 1) - 1) & 1);
-            st_row_chunks(smem_u32(sDS + (j & 1) * kBwPBytes), row, half, dsk);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ds_full[j & 1]);
-        }
-        mbar_wait(done, 0);
-        tc_fence_after();
-        uint32_t r[32];
-        float v[32];
-        tmem_ld_32x32(tmem_dq + lane_sel + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]) * p.scale;
-        if (qrow < p.S) store_row32_bf16(p.dq + ((long long)b * p.S + qrow) * p.ld_dqkv + h * kTcD + half * 32, v);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp_idx == 1) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
-// =====================================================================================================
-// Backward, v3: the same two kernels cut down so that TWO CTAs share an SM (192 threads, <= 98 KB shared memory,
-// 256 TMEM columns each), for the reason given at the v3 forward: the elementwise stage (ex2, dS) sets the pace and a
-// single CTA's 8 lock-stepped warps leave both the MUFU and the tensor pipe idle in turns.  One elementwise THREAD
-// per tile row handles the step's 64 columns as two 32-column halves; S/dP (TMEM) and P/dS (smem) are single
-// buffers — the overlap now comes from the co-resident CTA — and the Q/dO (K/V) ring has two stages.
-//   s_free: the elementwise warps have copied S/dP of the step out of TMEM -> the issuer may overwrite them.
-// =====================================================================================================
+// S/dP (TMEM) and P/dS (smem) are single buffers — the overlap comes from the co-resident CTA.
+//   s_free / st_free: the elementwise warps have copied S/dP of the step out of TMEM -> the issuer may overwrite them.
 constexpr int kB3Stages = 2;
 constexpr int kB3Threads = 6 * 32;
 // dK/dV kernel: two ring stages.  A third stage (with a single statistics buffer to stay under 113 KB) was measured
@@ -1294,14 +730,12 @@ int make_tmap_bsd(CUtensorMap* map, const void* base, int B, int S, int cols, lo
 }
 
 int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
-    CUtensorMap tq, tk, tv;
+    CUtensorMap tq, tk64, tv64;
     const int cols = a->nh * kTcD;
     int rc = make_tmap_bsd(&tq, a->q, a->B, a->S, cols, a->ld_qkv, kTcQ);
     if (rc) return rc;
-    rc = make_tmap_bsd(&tk, a->k, a->B, a->S, cols, a->ld_qkv, kTcKV);
-    if (rc) return rc;
-    rc = make_tmap_bsd(&tv, a->v, a->B, a->S, cols, a->ld_qkv, kTcKV);
-    if (rc) return rc;
+    if ((rc = make_tmap_bsd(&tk64, a->k, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
+    if ((rc = make_tmap_bsd(&tv64, a->v, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
     AttnTcDev d;
     d.o = reinterpret_cast<__nv_bfloat16*>(a->o);
     d.ld_o = a->ld_o;
@@ -1309,23 +743,12 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale_log2 = a->scale * kTcLog2e;
     static bool attr_done = false;
-    static int use_v2 = 0;
     if (!attr_done) {
-        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
         TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
-        const char* e = getenv("TAVK_ATTN_FWD_V2");    // A/B switch for profiling: the one-CTA-per-SM 128-key kernel
-        use_v2 = (e != nullptr && e[0] == '1');
         attr_done = true;
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
-    if (use_v2) {
-        TAVK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(grid), dim3(kTcThreads), (size_t)(kTcSmem), stream, tq, tk, tv, d));
-    } else {
-        CUtensorMap tk64, tv64;
-        if ((rc = make_tmap_bsd(&tk64, a->k, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
-        if ((rc = make_tmap_bsd(&tv64, a->v, a->B, a->S, cols, a->ld_qkv, kF3KV))) return rc;
-        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
-    }
+    TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1368,27 +791,14 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e;
     d.dbq = a->dbq; d.dbk = a->dbk; d.dbv = a->dbv;
     static bool attr_done = false;
-    static int use_v2 = 0;
     if (!attr_done) {
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
         TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
         TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
-        const char* e = getenv("TAVK_ATTN_BWD_V2");    // A/B switch for profiling: the one-CTA-per-SM kernels
-        use_v2 = (e != nullptr && e[0] == '1');
         attr_done = true;
     }
     dim3 grid((a->S + 127) / 128, a->nh, a->B);
-    if (use_v2) {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDkvSmem), stream, tq64, tk128, tv128, tdo64, d));
-        TAVK_CUDA(cudaGetLastError());
-        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc_kernel, dim3(grid), dim3(kBwThreads), (size_t)(kDqSmem), stream, tq128, tk64, tv64, tdo128, d));
-        return attn_bias_grads_by_colsum(a, stream);
-    } else {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-        TAVK_CUDA(cudaGetLastError());
-        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
-    }
+    TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
