@@ -11,6 +11,8 @@
   with flipped/transposed weights (dgrad) and a split-K wgrad.  cuDNN ran this as 32 tiny TF32 kernels per call
   (≈20 ms of a 90 ms step at B=16).
 """
+import weakref
+
 import torch
 import torch.nn.functional as F
 
@@ -158,22 +160,25 @@ def feature_extractor(w2v, wav):
 
 
 # ------------------------------------------------------------------------------------------------ patch embedding
-_cols_cache = {"key": None, "cols": None}
+_cols_cache = {"src": None, "key": None, "cols": None}
 
 
 def video_patches_bf16(pixel_values, tubelet, patch):
     """[B, T, C, H, W] -> bf16 [B, (T/tub)(H/p)(W/p), C*tub*p*p] in Conv3d weight order (c, dt, dy, dx); cached for
-    the second consumer of the same clip within a step."""
-    key = (pixel_values.data_ptr(), pixel_values._version, tuple(pixel_values.shape), tubelet, patch)
-    if _cols_cache["key"] == key:
+    the second consumer of the SAME tensor within a step (PreFormer and TAVForMAE read the same clip).  The cache is
+    keyed on the tensor object (weak reference) and its version counter, never on its address: the allocator hands the
+    block of a freed clip to the next batch, which then has the same data_ptr, shape and version 0."""
+    src = _cols_cache["src"]
+    key = (pixel_values._version, tubelet, patch)
+    if src is not None and src() is pixel_values and _cols_cache["key"] == key:
         return _cols_cache["cols"]
     B, T, C, H, W = pixel_values.shape
     tp, hp, wp = T // tubelet, H // patch, W // patch
-    v = pixel_values.view(B, tp, tubelet, C, hp, patch, wp, patch).permute(0, 1, 4, 6, 3, 2, 5, 7)
+    v = pixel_values.reshape(B, tp, tubelet, C, hp, patch, wp, patch).permute(0, 1, 4, 6, 3, 2, 5, 7)
     cols = torch.empty((B, tp, hp, wp, C, tubelet, patch, patch), dtype=torch.bfloat16, device=pixel_values.device)
     cols.copy_(v)  # one fused cast + permute pass over the clip
     cols = cols.view(B, tp * hp * wp, C * tubelet * patch * patch)
-    _cols_cache["key"], _cols_cache["cols"] = key, cols
+    _cols_cache["src"], _cols_cache["key"], _cols_cache["cols"] = weakref.ref(pixel_values), key, cols
     return cols
 
 

@@ -15,6 +15,7 @@ MELD_CLASS_WEIGHTS = [0.5285, 0.8794, 0.9732, 0.9316, 0.8255, 0.9729, 0.8890]
 CONFIGS = {
     "C1": dict(B=2, T=32, L=16000, K=104, C=7),     # BASELINE.json configs[0]: CPU-runnable case
     "C2": dict(B=16, T=70, L=48000, K=104, C=7),    # configs[1]: MELD 7-class, batch 16 (the benched workload)
+    "C3": dict(B=8, T=70, L=240000, K=104, C=7),    # configs[2]: IEMOCAP-shape 15 s audio (full TAV, fused S=923)
     "C4": dict(B=32, T=70, L=80000, K=104, C=2),    # configs[3]: MUStARD++ shape
 }
 

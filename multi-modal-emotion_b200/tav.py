@@ -21,9 +21,11 @@ _FP16_MIN = torch.finfo(torch.float16).min
 
 
 def set_encoder_variant(name):
-    """"reference" | "baseline" | "tiny" — sizes of the three HF encoders built by the next constructors."""
+    """"reference" | "baseline" | "tiny" | "tiny_base" — sizes of the three HF encoders built by the next constructors
+    ("tiny" = two layers of the reference families, "tiny_base" = two layers of the baseline families, i.e. the
+    group-norm Wav2Vec2-base conv stack the benchmark runs)."""
     global _VARIANT
-    if name not in ("reference", "baseline", "tiny"):
+    if name not in ("reference", "baseline", "tiny", "tiny_base"):
         raise ValueError(name)
     _VARIANT = name
 
@@ -44,6 +46,9 @@ def encoder_configs(variant=None):
     if variant == "baseline":    # roberta-base + wav2vec2-base + videomae-base
         return {"text": RobertaConfig(num_hidden_layers=12, **rob), "audio": Wav2Vec2Config(**w2v),
                 "video": VideoMAEConfig()}
+    if variant == "tiny_base":
+        return {"text": RobertaConfig(num_hidden_layers=2, **rob), "audio": Wav2Vec2Config(num_hidden_layers=2, **w2v),
+                "video": VideoMAEConfig(num_hidden_layers=2)}
     return {"text": RobertaConfig(num_hidden_layers=2, **rob),
             "audio": Wav2Vec2Config(num_hidden_layers=2, **large, **w2v), "video": VideoMAEConfig(num_hidden_layers=2)}
 

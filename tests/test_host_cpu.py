@@ -73,7 +73,7 @@ def test_synthetic_batch_format_and_masks():
     assert labels.tolist() == [0.0, 3.0]
     again, _ = syn.make_batch("C1")
     assert torch.equal(inputs[2]["visual_embeds"], again[2]["visual_embeds"])       # deterministic
-    assert syn.fused_len("C1") == 185 and syn.fused_len("C2") == 323 and syn.fused_len("C4") == 423
+    assert syn.fused_len("C1") == 185 and syn.fused_len("C2") == 323 and syn.fused_len("C4") == 423 and syn.fused_len("C3") == 923
     m = syn.reference_masks(2, 32, 49, 104, torch.tensor([32, 20]), torch.tensor([49, 37]))
     assert m.shape == (2, 1, 1, 185)
     assert sorted(set(m[..., :32].flatten().tolist())) == [-65504.0, 0.0]            # text: (1-m)*fp16.min
@@ -123,3 +123,42 @@ def test_wgrad_split_heuristic_and_layer_spec():
     assert len(engine.PARAM_SLOTS) == engine.N_SLOTS == 16
     s = engine.LayerSpec()
     assert s.pre_ln and s.mask_mode == "none" and s.hidden == 768
+
+
+def test_video_patch_cache_never_serves_a_recycled_address():
+    """frontends.video_patches_bf16 shares the patchified clip between PreFormer and TAVForMAE.  The allocator gives
+    the block of a freed clip to the next batch (same address, shape and version 0), which must NOT hit the cache:
+    the eager training loop would otherwise keep training on the first batch's video."""
+    import torch
+    import torch.nn.functional as F
+
+    from multi_modal_emotion_b200 import frontends
+
+    def ref(v):  # Conv3d(kernel = stride = (2,16,16)) im2col in weight order (c, dt, dy, dx)
+        B = v.shape[0]
+        u = v.permute(0, 2, 1, 3, 4)                                     # [B, C, T, H, W]
+        u = u.unfold(2, 2, 2).unfold(3, 16, 16).unfold(4, 16, 16)        # [B, C, T/2, H/16, W/16, 2, 16, 16]
+        return u.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B, -1, 3 * 2 * 16 * 16).bfloat16()
+
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(1, 4, 3, 32, 32, generator=g)
+    ca = frontends.video_patches_bf16(a, 2, 16)
+    assert torch.equal(ca, ref(a)) and frontends.video_patches_bf16(a, 2, 16) is ca      # same tensor: shared
+    w = torch.randn(8, 3, 2, 16, 16, generator=g)
+    conv = F.conv3d(a.permute(0, 2, 1, 3, 4), w, stride=(2, 16, 16)).flatten(2).transpose(1, 2)
+    assert (ca.float() @ w.reshape(8, -1).t() - conv).abs().max().item() < 0.5           # bf16 rounding of 1536 terms
+    ptr = a.data_ptr()
+    del a
+    for _ in range(8):                                                   # provoke address reuse
+        b = torch.randn(1, 4, 3, 32, 32, generator=g)
+        cb = frontends.video_patches_bf16(b, 2, 16)
+        assert torch.equal(cb, ref(b))
+        hit = b.data_ptr() == ptr
+        ptr = b.data_ptr()
+        del b
+        if hit:
+            break
+    c = torch.randn(1, 4, 3, 32, 32, generator=g)
+    cc = frontends.video_patches_bf16(c, 2, 16)
+    c.add_(1.0)                                                          # in-place write: version counter moves
+    assert torch.equal(frontends.video_patches_bf16(c, 2, 16), ref(c))
