@@ -47,6 +47,14 @@ TAVK_DEVINL void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+TAVK_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 TAVK_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 32 fp32 accumulator columns of this thread's row -> bf16 -> 64 contiguous bytes in global
@@ -80,6 +88,10 @@ constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 2 * kF3PBytes + 256
 constexpr int kF3Threads = 6 * 32;
 constexpr uint32_t kF3TmemCols = 256;
 
+// kTS: P goes back into TENSOR memory (bf16 pairs, 32 of the 64 spare columns per buffer) and the PV MMA reads its A
+// operand from there: no P staging in shared memory (16 stores per thread, a proxy fence) and no P operand fetch by the
+// tensor core (the kernels were paced by the shared-memory pipe, profiles/r1_ncu_attention_smem_pipe.txt).
+template <bool kTS>
 __global__ void __launch_bounds__(kF3Threads, 2)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
@@ -120,6 +132,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_o = tmem_base + 2 * kF3KV;
+    const uint32_t tmem_p = tmem_base + 3 * kF3KV;     // kTS: two bf16 P buffers of 32 columns each
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -166,9 +179,14 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const uint64_t dp = dp0 + (uint64_t)((j & 1) * (kF3PBytes >> 4));
                 const uint64_t dv = dv0 + (uint64_t)(st * (kF3KTile >> 4));
 #pragma unroll
-                for (int k = 0; k < kF3KV / 16; ++k)
-                    umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv,
-                              (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kF3KV / 16; ++k) {
+                    if constexpr (kTS)
+                        umma_bf16_ts(tmem_o, tmem_p + (uint32_t)((j & 1) * 32 + k * 8), dv + (uint64_t)(k * (2048 >> 4)),
+                                     idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    else
+                        umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv,
+                                  (j > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&kv_empty[st]);
                 umma_commit(&p_empty[j & 1]);
                 umma_commit(pv_done);
@@ -226,13 +244,17 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             l += (sum0 + sum1) + (sum2 + sum3);
             // P[j&1] must no longer be read by PV(j-2)
             if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
-            const uint32_t pbase = smem_u32(sP + (j & 1) * kF3PBytes) + row * 128;
+            if constexpr (kTS) {
+                tmem_st_32x32(tmem_p + lane_sel + (uint32_t)((j & 1) * 32), reinterpret_cast<uint32_t(&)[32]>(sr[0]));
+            } else {
+                const uint32_t pbase = smem_u32(sP + (j & 1) * kF3PBytes) + row * 128;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
-                             "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
-                             : "memory");
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
+                                 "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
+                                 : "memory");
+                }
             }
             // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
@@ -248,9 +270,10 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
                     tmem_st_32x32(to, orow);
                 }
-                tmem_st_wait();
+                if constexpr (!kTS) tmem_st_wait();
             }
-            fence_proxy_async_smem();   // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
+            if constexpr (kTS) tmem_st_wait();            // P (and a rescaled O) are in tensor memory
+            else fence_proxy_async_smem();                // generic-proxy smem writes of P -> visible to the tensor core
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[j & 1]);
@@ -307,9 +330,19 @@ struct AttnTcBwdDev {
     long long ld_dqkv;
     const float *dv_rowscale, *dv_rank1;
     int B, S, nh;
-    float scale, scale_log2;
+    float scale, scale_log2, inv_scale;
     float *dbq, *dbk, *dbv;      // optional bias-gradient accumulators (column sums of dq / dk / dv), f32 [nh*64]
 };
+
+// a -> {hi, lo, lo2, 0, 0, 0, 0, 0} bf16 with hi + lo + lo2 = a to 24 bits: one 16-byte chunk of a statistics row
+TAVK_DEVINL uint4 split3_bf16(float a) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(a);
+    const float r = a - __bfloat162float(h);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r);
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(r - __bfloat162float(l));
+    return make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16),
+                      (uint32_t)__bfloat16_as_ushort(l2), 0u, 0u);
+}
 
 // 32 packed-pair registers (= 64 bf16... here 16 regs = 32 bf16) -> this row's 4 swizzled 16-byte chunks
 TAVK_DEVINL void st_row_chunks(uint32_t tile_base, int row, int half, const uint32_t (&pk)[16]) {
@@ -328,11 +361,37 @@ constexpr int kB3Stages = 2;
 constexpr int kB3Threads = 6 * 32;
 // dK/dV kernel: two ring stages.  A third stage (with a single statistics buffer to stay under 113 KB) was measured
 // slower (346 vs 332 us at B=16 S=1464): unlike the dQ kernel its pace is not set by the TMA look-ahead.
-constexpr int kDkv3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + 2 * kBwPBytes + kB3Stages * 128 * 4 + 1024 + 256;
+// Per-query statistics enter the dK/dV kernel through the tensor core (kAug): S^T and dP^T get one extra K = 16 step
+//   S^T += 1 * (-lse_q / scale),   dP^T += 1 * (-delta_q)
+// with A = a [128][16] tile of ones and B = a [64 queries][16] tile whose row q holds the statistic split into three
+// bf16 terms (hi + lo + lo2 carries 24 mantissa bits; the ones make the sum independent of WHERE in the row they sit, so
+// the 16-byte chunk swizzle of the layout does not matter).  Why: thread = key row, so every thread needed all 64 lse
+// and 64 delta values of a step, and a broadcast shared-memory load costs one wavefront per 4 bytes — ncu counted 598
+// load + 319 store + 768 tensor-operand wavefronts per step = the kernel's whole duration (shared-memory pipe 100 %
+// busy, profiles/r1_ncu_attention_smem_pipe.txt).  The extra k-steps read 96 wavefronts instead of the 598.
+constexpr int kAugRow = 32;                              // bytes per row of a 16 x bf16 operand slice (SWIZZLE_32B)
+constexpr int kAugOnes = 128 * kAugRow;                  // 4 KB
+constexpr int kAugX = kBwStep * kAugRow;                 // 2 KB per statistic per stage
+constexpr int kDkv3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + 2 * kBwPBytes + kAugOnes + kB3Stages * 2 * kAugX + 1024 + 256;
 constexpr int kDq3Stages = 4;             // K_j/V_j ring of the dQ kernel: three steps of TMA look-ahead (2 stages: 258 us,
                                           // 3 stages: 208 us at B=16 S=1464 — the ring depth, not the math, set the pace)
 constexpr int kDq3Smem = 2 * kTcTile + kDq3Stages * 2 * kBwSmall + kBwPBytes + 256;
 
+// Development-only event trace (tools/attn_trace.py builds a private copy of the library with -DTAVK_ATTN_TRACE): the
+// chosen CTAs write clock64() at each hand-off of every step; compiled out of libtavk.so.
+#ifdef TAVK_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;
+constexpr int kTraceSlots = 16, kTraceCtas = 8, kTraceFirst = 1000;
+#define TAVK_TRACE(step, slot)                                                                                      \
+    do {                                                                                                            \
+        if (trace_cta >= 0 && g_attn_trace != nullptr && (threadIdx.x & 31) == 0)                                   \
+            g_attn_trace[((long long)trace_cta * 64 + (step)) * kTraceSlots + (slot)] = clock64();                  \
+    } while (0)
+#else
+#define TAVK_TRACE(step, slot) do { } while (0)
+#endif
+
+template <bool kAug, bool kDyn>
 __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -346,8 +405,11 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     uint8_t* sDO = sQ + kB3Stages * kBwSmall;         // ring: [stage] dO_i
     uint8_t* sP = sDO + kB3Stages * kBwSmall;         // P^T
     uint8_t* sDS = sP + kBwPBytes;                    // dS^T
-    float* s_stats = reinterpret_cast<float*>(sDS + kBwPBytes);   // ring: [stage][64 lse*log2e | 64 delta]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + kB3Stages * 128);
+    uint8_t* sOnes = sDS + kBwPBytes;                 // kAug: [128][16] bf16 ones (A operand of the statistics k-step)
+    uint8_t* sXL = sOnes + kAugOnes;                  // kAug ring: [stage][64 queries][16] bf16, row q = split(-lse_q / scale)
+    uint8_t* sXD = sXL + kB3Stages * kAugX;           // kAug ring: [stage][64 queries][16] bf16, row q = split(-delta_q)
+    float* s_stats = reinterpret_cast<float*>(sXL);   // !kAug ring: [stage][64 lse*log2e | 64 delta]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sXD + kB3Stages * kAugX);
     uint64_t* kv_full = bars;
     uint64_t* qdo_full = bars + 1;
     uint64_t* qdo_empty = qdo_full + kB3Stages;
@@ -361,6 +423,16 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_steps = (p.S + kBwStep - 1) / kBwStep;
+#ifdef TAVK_ATTN_TRACE
+    const int lin_cta = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+    const int trace_cta = (lin_cta >= kTraceFirst && lin_cta < kTraceFirst + kTraceCtas) ? lin_cta - kTraceFirst : -1;
+    if (trace_cta >= 0 && threadIdx.x == 0 && g_attn_trace != nullptr) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_trace[((long long)trace_cta * 64 + 63) * kTraceSlots] = smid;
+        g_attn_trace[((long long)trace_cta * 64 + 63) * kTraceSlots + 1] = clock64();
+    }
+#endif
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
@@ -371,6 +443,11 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_fence_init();
     }
     if (warp_idx == 1) tmem_alloc<256>(tmem_ptr_smem);
+    if constexpr (kAug) {
+        for (int c = threadIdx.x; c < kAugOnes / 16; c += kB3Threads)
+            reinterpret_cast<uint4*>(sOnes)[c] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -388,6 +465,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int i = 0; i < n_steps; ++i) {
             const int st = i % kB3Stages;
             mbar_wait_backoff<128>(&qdo_empty[st], ((i / kB3Stages) & 1) ^ 1);
+            TAVK_TRACE(i, 0);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&qdo_full[st], 2 * kBwSmall);
                 tma_load_3d(sQ + st * kBwSmall, &tmap_q, &qdo_full[st], h * kTcD, i * kBwStep, b);
@@ -397,11 +475,23 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int t = lane; t < kBwStep; t += 32) {
                 const int qi = i * kBwStep + t;
                 const bool ok = qi < p.S;
-                s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
-                s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
+                if constexpr (kAug) {
+                    // (S^T - lse/scale) * scale*log2e = S^T*scale*log2e - lse*log2e; queries >= S: -1e30 -> P = 0
+                    uint4* xl = reinterpret_cast<uint4*>(sXL + st * kAugX + t * kAugRow);
+                    uint4* xd = reinterpret_cast<uint4*>(sXD + st * kAugX + t * kAugRow);
+                    xl[0] = split3_bf16(ok ? -__ldg(p.lse + stat_off + qi) * p.inv_scale : -1.0e30f);
+                    xl[1] = make_uint4(0u, 0u, 0u, 0u);
+                    xd[0] = split3_bf16(ok ? -__ldg(p.delta + stat_off + qi) : 0.f);
+                    xd[1] = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
+                    s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
+                }
             }
+            if constexpr (kAug) fence_proxy_async_smem();   // the statistics rows are read by the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&qdo_full[st]);
+            TAVK_TRACE(i, 1);
         }
     } else if (warp_idx == 1) {
         const bool leader = elect_one();
@@ -411,42 +501,95 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const uint64_t dQk0 = umma_smem_desc(smem_u32(sQ), 16, 1024), dDOk0 = umma_smem_desc(smem_u32(sDO), 16, 1024);
         const uint64_t dQm0 = umma_smem_desc(smem_u32(sQ), 8192, 1024), dDOm0 = umma_smem_desc(smem_u32(sDO), 8192, 1024);
         const uint64_t dP0 = umma_smem_desc(smem_u32(sP), 16, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        const uint64_t dOnes = umma_smem_desc_sw32(smem_u32(sOnes), 256);
+        const uint64_t dXL0 = umma_smem_desc_sw32(smem_u32(sXL), 256), dXD0 = umma_smem_desc_sw32(smem_u32(sXD), 256);
         mbar_wait(kv_full, 0);
         tc_fence_after();
+        // S^T / dP^T of step i1 (needs the step's Q/dO stage and the elementwise warps' copy of step i1-1 out of TMEM)
+        auto issue_scores = [&](int i) {
+            const int st = i % kB3Stages;
+            const uint64_t so = (uint64_t)(st * (kBwSmall >> 4)), sx = (uint64_t)(st * (kAugX >> 4));
+            const uint32_t t_st = tmem_base, t_dp = tmem_base + 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+            if constexpr (kAug) umma_bf16(t_st, dOnes, dXL0 + sx, idesc_kk, 1u);    // S^T -= lse_q / scale
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
+            if constexpr (kAug) umma_bf16(t_dp, dOnes, dXD0 + sx, idesc_kk, 1u);    // dP^T -= delta_q
+            umma_commit(st_full);
+        };
+        // dV / dK of step `kstep` (needs its P^T / dS^T staged); frees the step's Q/dO stage and the P^T/dS^T buffers
+        auto issue_grads = [&](int kstep) {
+            const int st = kstep % kB3Stages;
+            const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_dv, dP0 + 2 * k, dDOm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_dk, dDS0 + 2 * k, dQm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&qdo_empty[st]);
+            umma_commit(pds_empty);
+        };
+        if constexpr (kDyn) {
+            // Whichever is ready first.  With a two-stage Q/dO ring the reload of a stage (TMA round trip + statistics,
+            // ~1400 cycles measured) starts when dV/dK of step i-1 complete; in program order S^T(i+1) -> dV/dK(i) the
+            // issuer sat in the wait for that reload while P^T/dS^T of step i were already staged, which delayed the
+            // NEXT reload in turn (tools/attn_trace.py timeline: the whole period was this chain).
+            int i1 = 0, i2 = 0;
+            uint32_t idle = 0;
+            while (i2 < n_steps) {
+                bool did = false;
+                if (i2 < i1 && mbar_test_warp(pds_full, i2 & 1)) {
+                    TAVK_TRACE(i2, 5);
+                    tc_fence_after();
+                    if (leader) issue_grads(i2);
+                    __syncwarp();
+                    TAVK_TRACE(i2, 6);
+                    ++i2;
+                    did = true;
+                }
+                if (i1 < n_steps && mbar_test_warp(&qdo_full[i1 % kB3Stages], (i1 / kB3Stages) & 1) &&
+                    (i1 == 0 || mbar_test_warp(st_free, (i1 - 1) & 1))) {
+                    TAVK_TRACE(i1, 3);
+                    tc_fence_after();
+                    if (leader) issue_scores(i1);
+                    __syncwarp();
+                    TAVK_TRACE(i1, 4);
+                    ++i1;
+                    did = true;
+                }
+                if (!did) {
+                    __nanosleep(20);
+                    if (++idle > (1u << 26)) {
+                        if (lane == 0) printf("tavk: dK/dV issuer stalled (block %d, i1 %d, i2 %d)\n", (int)blockIdx.x, i1, i2);
+                        __trap();
+                    }
+                }
+            }
+        } else {
         for (int i = 0; i <= n_steps; ++i) {
             if (i < n_steps) {
                 const int st = i % kB3Stages;
                 mbar_wait_backoff<32>(&qdo_full[st], (i / kB3Stages) & 1);
+                TAVK_TRACE(i, 2);
                 if (i >= 1) mbar_wait_backoff<32>(st_free, (i - 1) & 1);
+                TAVK_TRACE(i, 3);
                 tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
-                    const uint32_t t_st = tmem_base, t_dp = tmem_base + 64;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-                    umma_commit(st_full);
-                }
+                if (leader) issue_scores(i);
                 __syncwarp();
+                TAVK_TRACE(i, 4);
             }
             if (i >= 1) {
-                const int kstep = i - 1, st = kstep % kB3Stages;
+                const int kstep = i - 1;
                 mbar_wait_backoff<32>(pds_full, kstep & 1);
+                TAVK_TRACE(kstep, 5);
                 tc_fence_after();
-                if (leader) {
-                    const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dv, dP0 + 2 * k, dDOm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dk, dDS0 + 2 * k, dQm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&qdo_empty[st]);
-                    umma_commit(pds_empty);
-                }
+                if (leader) issue_grads(kstep);
                 __syncwarp();
+                TAVK_TRACE(kstep, 6);
             }
+        }
         }
         if (leader) umma_commit(done);
         __syncwarp();
@@ -456,9 +599,47 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int i = 0; i < n_steps; ++i) {
             const int stg = i % kB3Stages;
-            mbar_wait(&qdo_full[stg], (i / kB3Stages) & 1);        // the step's statistics are staged
+            if constexpr (!kAug) mbar_wait(&qdo_full[stg], (i / kB3Stages) & 1);   // the step's statistics are staged
+            if (quarter == 0) TAVK_TRACE(i, 7);
             mbar_wait(st_full, i & 1);
+            if (quarter == 0) TAVK_TRACE(i, 8);
             tc_fence_after();
+            if constexpr (kAug) {
+                // all 128 accumulator words of the row first, so the issuer can overwrite S^T / dP^T (step i+1) while
+                // this step's ex2 / products / stores run
+                uint32_t s0[32], s1[32], d0[32], d1[32];
+                tmem_ld_32x32(tmem_base + lane_sel, s0);
+                tmem_ld_32x32(tmem_base + lane_sel + 32, s1);
+                tmem_ld_32x32(tmem_base + lane_sel + 64, d0);
+                tmem_ld_32x32(tmem_base + lane_sel + 96, d1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(st_free);
+                if (quarter == 0) TAVK_TRACE(i, 9);
+                uint32_t pk[16], dsk[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ex2_approx(__uint_as_float(s0[c]) * p.scale_log2);
+                    const float p1 = ex2_approx(__uint_as_float(s0[c + 1]) * p.scale_log2);
+                    pk[c >> 1] = pack_bf16x2(p0, p1);
+                    dsk[c >> 1] = pack_bf16x2(p0 * __uint_as_float(d0[c]), p1 * __uint_as_float(d0[c + 1]));
+                }
+                if (quarter == 0) TAVK_TRACE(i, 10);
+                if (i >= 1) mbar_wait(pds_empty, (i - 1) & 1);   // dV/dK MMAs of step i-1 have read P^T/dS^T
+                if (quarter == 0) TAVK_TRACE(i, 11);
+                st_row_chunks(smem_u32(sP), row, 0, pk);
+                st_row_chunks(smem_u32(sDS), row, 0, dsk);
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ex2_approx(__uint_as_float(s1[c]) * p.scale_log2);
+                    const float p1 = ex2_approx(__uint_as_float(s1[c + 1]) * p.scale_log2);
+                    pk[c >> 1] = pack_bf16x2(p0, p1);
+                    dsk[c >> 1] = pack_bf16x2(p0 * __uint_as_float(d1[c]), p1 * __uint_as_float(d1[c + 1]));
+                }
+                st_row_chunks(smem_u32(sP), row, 1, pk);
+                st_row_chunks(smem_u32(sDS), row, 1, dsk);
+            } else {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t s[32], dp[32];
@@ -469,10 +650,21 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(st_free);
+                    if (quarter == 0) TAVK_TRACE(i, 9);
                 }
+                uint32_t pk[16], dsk[16];
+                if constexpr (kAug) {
+                    // the statistics are already inside the accumulators: P^T = ex2(S^T c), dS^T = P^T dP^T
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        const float p0 = ex2_approx(__uint_as_float(s[c]) * p.scale_log2);
+                        const float p1 = ex2_approx(__uint_as_float(s[c + 1]) * p.scale_log2);
+                        pk[c >> 1] = pack_bf16x2(p0, p1);
+                        dsk[c >> 1] = pack_bf16x2(p0 * __uint_as_float(dp[c]), p1 * __uint_as_float(dp[c + 1]));
+                    }
+                } else {
                 // per-query statistics of the 32 columns: broadcast LDS.128 from the producer's staging ring
                 const uint32_t st_addr = smem_u32(s_stats + stg * 128 + half * 32);
-                uint32_t pk[16], dsk[16];
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     const float4 l4 = ld_shared_v4(st_addr + c * 4), d4 = ld_shared_v4(st_addr + 256 + c * 4);
@@ -485,14 +677,20 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - d4.x), p1 * (__uint_as_float(dp[c + 1]) - d4.y));
                     dsk[(c >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[c + 2]) - d4.z), p3 * (__uint_as_float(dp[c + 3]) - d4.w));
                 }
+                }
+                if (half == 0 && quarter == 0) TAVK_TRACE(i, 10);
                 if (half == 0 && i >= 1) mbar_wait(pds_empty, (i - 1) & 1);   // dV/dK MMAs of step i-1 have read P^T/dS^T
+                if (half == 0 && quarter == 0) TAVK_TRACE(i, 11);
                 st_row_chunks(smem_u32(sP), row, half, pk);
                 st_row_chunks(smem_u32(sDS), row, half, dsk);
             }
+            }
+            if (quarter == 0) TAVK_TRACE(i, 12);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
+            if (quarter == 0) TAVK_TRACE(i, 13);
         }
         mbar_wait(done, 0);
         tc_fence_after();
@@ -529,6 +727,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
+template <bool kTS>   // kTS: dS goes back into tensor memory and is the A operand of the dQ MMA from there (see the forward)
 __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -570,6 +769,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_dq = tmem_base + 128;
+    const uint32_t tmem_ds = tmem_base + 192;          // kTS: bf16 dS, 32 columns
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -617,8 +817,12 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_dq, dDS0 + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (kTS)
+                            umma_bf16_ts(tmem_dq, tmem_ds + (uint32_t)(k * 8), dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                        else
+                            umma_bf16(tmem_dq, dDS0 + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
+                    }
                     umma_commit(&kv_empty[st]);
                     umma_commit(ds_empty);
                 }
@@ -669,9 +873,11 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     }
                 }
                 if (half == 0 && j >= 1) mbar_wait(ds_empty, (j - 1) & 1);   // the dQ MMAs of step j-1 have read dS
-                st_row_chunks(smem_u32(sDS), row, half, dsk);
+                if constexpr (kTS) tmem_st_32x16(tmem_ds + lane_sel + (uint32_t)(half * 16), dsk);
+                else st_row_chunks(smem_u32(sDS), row, half, dsk);
             }
-            fence_proxy_async_smem();
+            if constexpr (kTS) tmem_st_wait();
+            else fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
@@ -743,12 +949,20 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale_log2 = a->scale * kTcLog2e;
     static bool attr_done = false;
+    static bool ts = true;
     if (!attr_done) {
-        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+        const char* e = getenv("TAVK_ATTN_TS");
+        ts = !(e != nullptr && e[0] == '0');
+        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
         attr_done = true;
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
-    TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
+    if (ts) {
+        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel<true>, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
+    } else {
+        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel<false>, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
+    }
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -766,6 +980,13 @@ int attn_bias_grads_by_colsum(const tavk_attn_bwd_args* a, cudaStream_t stream) 
     }
     return 0;
 }
+
+#ifdef TAVK_ATTN_TRACE
+extern "C" int tavk_debug_set_attn_trace(void* buf) {
+    long long* pbuf = reinterpret_cast<long long*>(buf);
+    return cudaMemcpyToSymbol(g_attn_trace, &pbuf, sizeof(pbuf)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // delta must already hold rowsum(dO * O) (attention.cu: attn_delta_kernel)
 int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
@@ -788,17 +1009,39 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     d.ld_dqkv = a->ld_dqkv;
     d.dv_rowscale = a->dv_rowscale; d.dv_rank1 = a->dv_rank1;
     d.B = a->B; d.S = a->S; d.nh = a->nh;
-    d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e;
+    d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e; d.inv_scale = 1.0f / a->scale;
     d.dbq = a->dbq; d.dbk = a->dbk; d.dbv = a->dbv;
     static bool attr_done = false;
+    static int aug = 3;
+    static bool ts = true;
     if (!attr_done) {
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
+        const char* e = getenv("TAVK_DKV_AUG");
+        if (e != nullptr && e[0] >= '0' && e[0] <= '3') aug = e[0] - '0';
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        const char* e2 = getenv("TAVK_ATTN_TS");
+        ts = !(e2 != nullptr && e2[0] == '0');
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
         attr_done = true;
     }
     dim3 grid((a->S + 127) / 128, a->nh, a->B);
-    TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-    TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
+    if (aug == 3) {
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<true, true>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    } else if (aug == 2) {
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<true, false>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    } else if (aug == 1) {
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<false, true>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    } else {
+        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<false, false>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    }
+    if (ts) {
+        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel<true>, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
+    } else {
+        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel<false>, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
+    }
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

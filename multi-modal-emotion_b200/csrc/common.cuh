@@ -253,6 +253,20 @@ TAVK_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking, warp-uniform test (for a warp that polls several barriers and serves whichever completes first).
+TAVK_DEVINL bool mbar_test_warp(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return __all_sync(0xffffffffu, ok != 0);
+}
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
 TAVK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -322,6 +336,18 @@ TAVK_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, ui
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (M = 128 rows = TMEM lanes, K-major, two bf16 per 32-bit column, so
+// one K = 16 step is 8 columns) is read from tensor memory instead of shared memory.
+TAVK_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 TAVK_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -352,6 +378,17 @@ TAVK_DEVINL uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// Same for a K-major operand slice of 16 bf16 (32-byte rows) in the SWIZZLE_32B canonical layout: 8-row atoms of 256
+// bytes, `sbo_bytes` between atoms (256 when packed), layout = 6 (SW32); the tile base must be 256-byte aligned.
+TAVK_DEVINL uint64_t umma_smem_desc_sw32(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
     return d;
 }
 // UMMA instruction descriptor for kind::f16, bf16 x bf16 -> fp32.

@@ -1,0 +1,66 @@
+"""Event timeline of the dK/dV attention-backward kernel (development tool).
+
+Builds a PRIVATE copy of the library with -DTAVK_ATTN_TRACE (multi-modal-emotion_b200/build/libtavk_trace.so; libtavk.so
+itself has the trace compiled out), runs one backward at B=16, S=1464 and dumps clock64() stamps of every hand-off of
+every step for 8 CTAs to gpurun_out/attn_trace_<variant>.json.
+  python tools/attn_trace.py build            # here (no GPU)
+  TAVK_DKV_AUG=2 python tools/attn_trace.py   # on the GPU box"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from multi_modal_emotion_b200 import build_ext  # noqa: E402
+
+TRACE_LIB = os.path.join(build_ext.OBJ, "libtavk_trace.so")
+
+
+def build():
+    build_ext.build_library()
+    nvcc = build_ext._nvcc()
+    obj = os.path.join(build_ext.OBJ, "attention_tc_trace.o")
+    subprocess.run([nvcc] + build_ext.NVCC_FLAGS + ["-DTAVK_ATTN_TRACE", "-c", os.path.join(build_ext.CSRC, "attention_tc.cu"),
+                    "-o", obj], check=True)
+    objs = [os.path.join(build_ext.OBJ, s.replace(".cu", ".o")) for s in build_ext.SOURCES if s != "attention_tc.cu"] + [obj]
+    subprocess.run([nvcc, "-shared", "-cudart", "shared", "-o", TRACE_LIB] + objs, check=True)
+    print(TRACE_LIB)
+
+
+def run():
+    import ctypes
+
+    import torch
+
+    from multi_modal_emotion_b200 import _lib as L
+
+    L.LIB_PATH = TRACE_LIB
+    h = L.lib()
+    B, S, nh, H = 16, 1464, 12, 768
+    qkv = torch.randn(B, S, 3 * H, device="cuda").bfloat16()
+    q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+    o = torch.empty(B, S, H, device="cuda", dtype=torch.bfloat16)
+    do = torch.randn(B, S, H, device="cuda").bfloat16()
+    lse = torch.empty(B, nh, S, device="cuda")
+    delta = torch.empty_like(lse)
+    dqkv = torch.empty_like(qkv)
+    buf = torch.zeros(8 * 64 * 16, dtype=torch.int64, device="cuda")
+    fn = h.tavk_debug_set_attn_trace
+    fn.argtypes, fn.restype = [ctypes.c_void_p], ctypes.c_int
+    assert fn(buf.data_ptr()) == 0
+    L.attn_fwd(q, k, v, o, lse, B=B, S=S, nh=nh, ld_qkv=3 * H, ld_o=H)
+    for it in range(3):
+        buf.zero_()
+        L.attn_bwd(q, k, v, o, do, lse, delta, dqkv[..., :H], dqkv[..., H:2 * H], dqkv[..., 2 * H:], B=B, S=S, nh=nh,
+                   ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H)
+        torch.cuda.synchronize()
+    tag = os.environ.get("TAVK_DKV_AUG", "default")
+    out = os.path.join(ROOT, "gpurun_out", "attn_trace_%s.json" % tag)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(buf.view(8, 64, 16).cpu().tolist(), open(out, "w"))
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    build() if (len(sys.argv) > 1 and sys.argv[1] == "build") else run()
