@@ -9,11 +9,16 @@
 //   warp 0      TMA producer (3-D tensor maps over [B][S][row], SWIZZLE_128B, rows >= S zero-filled by the hardware)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (accumulators S / dP / O / dQ / dK / dV in TMEM)
 //   warps 2..5  elementwise: one thread per tile row (TMEM lane), tcgen05.ld -> ex2 / dS in registers -> bf16 P / dS
-//               staged in shared memory in the UMMA K-major SW128 layout for the next MMA
+//               handed to the next MMA as its A operand: through TENSOR memory (tcgen05.st into the 64 spare columns,
+//               tcgen05.mma with A in TMEM) in the forward and dQ kernels, through shared memory (UMMA K-major SW128
+//               layout) in the dK/dV kernel, whose 256 columns are all accumulators
 // Every kernel keeps within 113 KB of shared memory and 256 TMEM columns so that TWO CTAs share an SM: with d = 64 the
 // elementwise stage, not the tensor pipe, sets the pace (16 ex2/clk/SM against 8192 tensor FLOP/clk/SM), and two
 // independent CTAs keep each other's idle phases busy.  An earlier one-CTA-per-SM version (8 elementwise warps, 128-key
-// tiles, 2 threads per row) measured 286 / 386 / 294 us (fwd / dK,dV / dQ) at B=16, S=1464; these: 191 / 332 / 207 us.
+// tiles, 2 threads per row) measured 286 / 386 / 294 us (fwd / dK,dV / dQ) at B=16, S=1464; with P / dS staged in shared
+// memory 191 / 332 / 207 us; these 180 / 321 / 197 us.  What the shared-memory hand-off cost: with N = 64 an MMA's
+// operand fetch (6 KB at 128 B/clk) takes longer than its math (32 clk), and the P / dS stores plus the proxy fence
+// share that pipe (profiles/r1_ncu_attention_smem_pipe.txt).
 #include "../../include/tavk.h"
 #include <stdlib.h>
 
@@ -74,24 +79,20 @@ struct AttnTcDev {
 };
 
 // =====================================================================================================
-// Forward.  KV tile = 64 keys, 4-stage (K_j, V_j) ring; S double-buffered in TMEM (2 x 64 columns) + O (64 columns); P
-// double-buffered in smem (2 x 16 KB).  QK of tile j+1 is issued before PV of tile j, so the tensor pipe works while
-// tile j's softmax runs.  Online softmax without any shuffle (thread = row); lazy rescaling: the running max only moves
+// Forward.  KV tile = 64 keys, 4-stage (K_j, V_j) ring; TMEM: S double-buffered (2 x 64 columns), O (64 columns), bf16 P
+// double-buffered (2 x 32 columns, two keys per column): the softmax threads write P back with tcgen05.st and PV reads
+// its A operand from there — no P in shared memory, no proxy fence.  QK of tile j+1 is issued before PV of tile j, so
+// the tensor pipe works while tile j's softmax runs.  Online softmax without any shuffle (thread = row); lazy rescaling: the running max only moves
 // (and O in TMEM is only rescaled, tcgen05.ld/st) when it grows by more than 8 in the log2 domain.
 // Epilogue: O / l -> bf16 rows, lse = (m + log2 l) ln2.
 // =====================================================================================================
 constexpr int kF3KV = 64;
 constexpr int kF3Stages = 4;
 constexpr int kF3KTile = kF3KV * kTcD * 2;            // 8 KB (K or V tile)
-constexpr int kF3PBytes = kTcQ * kF3KV * 2;           // 16 KB
-constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 2 * kF3PBytes + 256;   // 112.25 KB: two CTAs per SM, no slack
+constexpr int kF3Smem = kTcTile + kF3Stages * 2 * kF3KTile + 256;   // 80.25 KB (two CTAs per SM)
 constexpr int kF3Threads = 6 * 32;
 constexpr uint32_t kF3TmemCols = 256;
 
-// kTS: P goes back into TENSOR memory (bf16 pairs, 32 of the 64 spare columns per buffer) and the PV MMA reads its A
-// operand from there: no P staging in shared memory (16 stores per thread, a proxy fence) and no P operand fetch by the
-// tensor core (the kernels were paced by the shared-memory pipe, profiles/r1_ncu_attention_smem_pipe.txt).
-template <bool kTS>
 __global__ void __launch_bounds__(kF3Threads, 2)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttnTcDev p) {
@@ -101,8 +102,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint8_t* sQ = smem;
     uint8_t* sK = smem + kTcTile;
     uint8_t* sV = sK + kF3Stages * kF3KTile;
-    uint8_t* sP = sV + kF3Stages * kF3KTile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kF3PBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kF3Stages * kF3KTile);
     uint64_t* q_full = bars;               // 1
     uint64_t* kv_full = bars + 1;          // kF3Stages
     uint64_t* kv_empty = kv_full + kF3Stages;
@@ -132,7 +132,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_o = tmem_base + 2 * kF3KV;
-    const uint32_t tmem_p = tmem_base + 3 * kF3KV;     // kTS: two bf16 P buffers of 32 columns each
+    const uint32_t tmem_p = tmem_base + 3 * kF3KV;     // two bf16 P buffers of 32 columns each
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -153,7 +153,6 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint64_t dq0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
         const uint64_t dk0 = umma_smem_desc(smem_u32(sK), 16, 1024);
         const uint64_t dv0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
-        const uint64_t dp0 = umma_smem_desc(smem_u32(sP), 16, 1024);
         auto issue_qk = [&](int j) {
             const int st = j % kF3Stages;
             mbar_wait_backoff<32>(&kv_full[st], (j / kF3Stages) & 1);
@@ -176,17 +175,11 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_after();
             if (leader) {
                 const int st = j % kF3Stages;
-                const uint64_t dp = dp0 + (uint64_t)((j & 1) * (kF3PBytes >> 4));
                 const uint64_t dv = dv0 + (uint64_t)(st * (kF3KTile >> 4));
 #pragma unroll
-                for (int k = 0; k < kF3KV / 16; ++k) {
-                    if constexpr (kTS)
-                        umma_bf16_ts(tmem_o, tmem_p + (uint32_t)((j & 1) * 32 + k * 8), dv + (uint64_t)(k * (2048 >> 4)),
-                                     idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                    else
-                        umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dv + (uint64_t)(k * (2048 >> 4)), idesc_pv,
-                                  (j > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < kF3KV / 16; ++k)   // A = P from tensor memory: 16 keys = 8 columns of bf16 pairs
+                    umma_bf16_ts(tmem_o, tmem_p + (uint32_t)((j & 1) * 32 + k * 8), dv + (uint64_t)(k * (2048 >> 4)),
+                                 idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[st]);
                 umma_commit(&p_empty[j & 1]);
                 umma_commit(pv_done);
@@ -244,18 +237,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             l += (sum0 + sum1) + (sum2 + sum3);
             // P[j&1] must no longer be read by PV(j-2)
             if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
-            if constexpr (kTS) {
-                tmem_st_32x32(tmem_p + lane_sel + (uint32_t)((j & 1) * 32), reinterpret_cast<uint32_t(&)[32]>(sr[0]));
-            } else {
-                const uint32_t pbase = smem_u32(sP + (j & 1) * kF3PBytes) + row * 128;
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const uint32_t addr = pbase + ((ch ^ (row & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sr[4 * ch]), "r"(sr[4 * ch + 1]),
-                                 "r"(sr[4 * ch + 2]), "r"(sr[4 * ch + 3])
-                                 : "memory");
-                }
-            }
+            tmem_st_32x32(tmem_p + lane_sel + (uint32_t)((j & 1) * 32), reinterpret_cast<uint32_t(&)[32]>(sr[0]));
             // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
                 mbar_wait(pv_done, (j - 1) & 1);
@@ -270,10 +252,8 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
                     tmem_st_32x32(to, orow);
                 }
-                if constexpr (!kTS) tmem_st_wait();
             }
-            if constexpr (kTS) tmem_st_wait();            // P (and a rescaled O) are in tensor memory
-            else fence_proxy_async_smem();                // generic-proxy smem writes of P -> visible to the tensor core
+            tmem_st_wait();            // P (and a rescaled O) are in tensor memory
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[j & 1]);
@@ -312,11 +292,11 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // =====================================================================================================
 // Backward (mask-free mode), two kernels that recompute P from the saved log-sum-exp:
 //   dK/dV kernel: CTA = 128 keys of one (b,h); loops over 64-query steps.
-//       S^T = K Q_i^T, dP^T = V dO_i^T               (UMMA 128x64x16 x4 each -> TMEM)
-//       P^T = ex2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)   (thread = key row, two 32-query halves)
+//       S^T = K Q_i^T - lse_q/c, dP^T = V dO_i^T - delta_q   (UMMA 128x64x16 x4 each + one statistics k-step -> TMEM)
+//       P^T = ex2(S^T c), dS^T = P^T dP^T                     (thread = key row)
 //       dV += P^T dO_i, dK += dS^T Q_i               (A = bf16 P^T / dS^T from smem, B = dO_i / Q_i MN-major)
 //   dQ kernel:    CTA = 128 queries; loops over 64-key steps.
-//       S = Q K_j^T, dP = dO V_j^T -> dS = ex2(S c - lse_row)(dP - delta_row) -> dQ += dS K_j
+//       S = Q K_j^T, dP = dO V_j^T -> dS = ex2(S c - lse_row)(dP - delta_row) -> dQ += dS K_j  (A = bf16 dS from TMEM)
 // No atomics in the data path, deterministic.  Queries >= S are neutralised with lse = +inf (P = 0), keys >= S by
 // zeroing P.  Optional: the q/k/v projection bias gradients (column sums of dQ / dK / dV) from the epilogues.
 // =====================================================================================================
@@ -359,23 +339,23 @@ TAVK_DEVINL void st_row_chunks(uint32_t tile_base, int row, int half, const uint
 //   s_free / st_free: the elementwise warps have copied S/dP of the step out of TMEM -> the issuer may overwrite them.
 constexpr int kB3Stages = 2;
 constexpr int kB3Threads = 6 * 32;
-// dK/dV kernel: two ring stages.  A third stage (with a single statistics buffer to stay under 113 KB) was measured
-// slower (346 vs 332 us at B=16 S=1464): unlike the dQ kernel its pace is not set by the TMA look-ahead.
-// Per-query statistics enter the dK/dV kernel through the tensor core (kAug): S^T and dP^T get one extra K = 16 step
+// dK/dV kernel: two ring stages (a third does not fit next to K, V, P^T and dS^T in 113 KB).
+// Per-query statistics enter the dK/dV kernel through the tensor core: S^T and dP^T get one extra K = 16 step
 //   S^T += 1 * (-lse_q / scale),   dP^T += 1 * (-delta_q)
 // with A = a [128][16] tile of ones and B = a [64 queries][16] tile whose row q holds the statistic split into three
 // bf16 terms (hi + lo + lo2 carries 24 mantissa bits; the ones make the sum independent of WHERE in the row they sit, so
 // the 16-byte chunk swizzle of the layout does not matter).  Why: thread = key row, so every thread needed all 64 lse
 // and 64 delta values of a step, and a broadcast shared-memory load costs one wavefront per 4 bytes — ncu counted 598
 // load + 319 store + 768 tensor-operand wavefronts per step = the kernel's whole duration (shared-memory pipe 100 %
-// busy, profiles/r1_ncu_attention_smem_pipe.txt).  The extra k-steps read 96 wavefronts instead of the 598.
+// busy, profiles/r1_ncu_attention_smem_pipe.txt).  The extra k-steps read 96 wavefronts instead of the 598.  On its own
+// this moved the bound to the issuer's program order (see the ready-first loop below): 332 -> 355 us; with it 321 us.
 constexpr int kAugRow = 32;                              // bytes per row of a 16 x bf16 operand slice (SWIZZLE_32B)
 constexpr int kAugOnes = 128 * kAugRow;                  // 4 KB
 constexpr int kAugX = kBwStep * kAugRow;                 // 2 KB per statistic per stage
 constexpr int kDkv3Smem = 2 * kTcTile + kB3Stages * 2 * kBwSmall + 2 * kBwPBytes + kAugOnes + kB3Stages * 2 * kAugX + 1024 + 256;
 constexpr int kDq3Stages = 4;             // K_j/V_j ring of the dQ kernel: three steps of TMA look-ahead (2 stages: 258 us,
                                           // 3 stages: 208 us at B=16 S=1464 — the ring depth, not the math, set the pace)
-constexpr int kDq3Smem = 2 * kTcTile + kDq3Stages * 2 * kBwSmall + kBwPBytes + 256;
+constexpr int kDq3Smem = 2 * kTcTile + kDq3Stages * 2 * kBwSmall + 256;
 
 // Development-only event trace (tools/attn_trace.py builds a private copy of the library with -DTAVK_ATTN_TRACE): the
 // chosen CTAs write clock64() at each hand-off of every step; compiled out of libtavk.so.
@@ -391,7 +371,6 @@ constexpr int kTraceSlots = 16, kTraceCtas = 8, kTraceFirst = 1000;
 #define TAVK_TRACE(step, slot) do { } while (0)
 #endif
 
-template <bool kAug, bool kDyn>
 __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -405,10 +384,9 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     uint8_t* sDO = sQ + kB3Stages * kBwSmall;         // ring: [stage] dO_i
     uint8_t* sP = sDO + kB3Stages * kBwSmall;         // P^T
     uint8_t* sDS = sP + kBwPBytes;                    // dS^T
-    uint8_t* sOnes = sDS + kBwPBytes;                 // kAug: [128][16] bf16 ones (A operand of the statistics k-step)
-    uint8_t* sXL = sOnes + kAugOnes;                  // kAug ring: [stage][64 queries][16] bf16, row q = split(-lse_q / scale)
-    uint8_t* sXD = sXL + kB3Stages * kAugX;           // kAug ring: [stage][64 queries][16] bf16, row q = split(-delta_q)
-    float* s_stats = reinterpret_cast<float*>(sXL);   // !kAug ring: [stage][64 lse*log2e | 64 delta]
+    uint8_t* sOnes = sDS + kBwPBytes;                 // [128][16] bf16 ones (A operand of the statistics k-step)
+    uint8_t* sXL = sOnes + kAugOnes;                  // ring: [stage][64 queries][16] bf16, row q = split(-lse_q / scale)
+    uint8_t* sXD = sXL + kB3Stages * kAugX;           // ring: [stage][64 queries][16] bf16, row q = split(-delta_q)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sXD + kB3Stages * kAugX);
     uint64_t* kv_full = bars;
     uint64_t* qdo_full = bars + 1;
@@ -443,11 +421,9 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_fence_init();
     }
     if (warp_idx == 1) tmem_alloc<256>(tmem_ptr_smem);
-    if constexpr (kAug) {
-        for (int c = threadIdx.x; c < kAugOnes / 16; c += kB3Threads)
-            reinterpret_cast<uint4*>(sOnes)[c] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-        fence_proxy_async_smem();
-    }
+    for (int c = threadIdx.x; c < kAugOnes / 16; c += kB3Threads)
+        reinterpret_cast<uint4*>(sOnes)[c] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -475,20 +451,15 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int t = lane; t < kBwStep; t += 32) {
                 const int qi = i * kBwStep + t;
                 const bool ok = qi < p.S;
-                if constexpr (kAug) {
-                    // (S^T - lse/scale) * scale*log2e = S^T*scale*log2e - lse*log2e; queries >= S: -1e30 -> P = 0
-                    uint4* xl = reinterpret_cast<uint4*>(sXL + st * kAugX + t * kAugRow);
-                    uint4* xd = reinterpret_cast<uint4*>(sXD + st * kAugX + t * kAugRow);
-                    xl[0] = split3_bf16(ok ? -__ldg(p.lse + stat_off + qi) * p.inv_scale : -1.0e30f);
-                    xl[1] = make_uint4(0u, 0u, 0u, 0u);
-                    xd[0] = split3_bf16(ok ? -__ldg(p.delta + stat_off + qi) : 0.f);
-                    xd[1] = make_uint4(0u, 0u, 0u, 0u);
-                } else {
-                    s_stats[st * 128 + t] = ok ? __ldg(p.lse + stat_off + qi) * kTcLog2e : INFINITY;   // +inf -> P = 0
-                    s_stats[st * 128 + 64 + t] = ok ? __ldg(p.delta + stat_off + qi) : 0.f;
-                }
+                // (S^T - lse/scale) * scale*log2e = S^T*scale*log2e - lse*log2e; queries >= S: -1e30 -> P = 0
+                uint4* xl = reinterpret_cast<uint4*>(sXL + st * kAugX + t * kAugRow);
+                uint4* xd = reinterpret_cast<uint4*>(sXD + st * kAugX + t * kAugRow);
+                xl[0] = split3_bf16(ok ? -__ldg(p.lse + stat_off + qi) * p.inv_scale : -1.0e30f);
+                xl[1] = make_uint4(0u, 0u, 0u, 0u);
+                xd[0] = split3_bf16(ok ? -__ldg(p.delta + stat_off + qi) : 0.f);
+                xd[1] = make_uint4(0u, 0u, 0u, 0u);
             }
-            if constexpr (kAug) fence_proxy_async_smem();   // the statistics rows are read by the tensor core
+            fence_proxy_async_smem();   // the statistics rows are read by the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&qdo_full[st]);
             TAVK_TRACE(i, 1);
@@ -512,10 +483,10 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             const uint32_t t_st = tmem_base, t_dp = tmem_base + 64;
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(t_st, dK + 2 * k, dQk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-            if constexpr (kAug) umma_bf16(t_st, dOnes, dXL0 + sx, idesc_kk, 1u);    // S^T -= lse_q / scale
+            umma_bf16(t_st, dOnes, dXL0 + sx, idesc_kk, 1u);    // S^T -= lse_q / scale
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(t_dp, dV + 2 * k, dDOk0 + so + 2 * k, idesc_kk, k > 0 ? 1u : 0u);
-            if constexpr (kAug) umma_bf16(t_dp, dOnes, dXD0 + sx, idesc_kk, 1u);    // dP^T -= delta_q
+            umma_bf16(t_dp, dOnes, dXD0 + sx, idesc_kk, 1u);    // dP^T -= delta_q
             umma_commit(st_full);
         };
         // dV / dK of step `kstep` (needs its P^T / dS^T staged); frees the step's Q/dO stage and the P^T/dS^T buffers
@@ -531,7 +502,7 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             umma_commit(&qdo_empty[st]);
             umma_commit(pds_empty);
         };
-        if constexpr (kDyn) {
+        {
             // Whichever is ready first.  With a two-stage Q/dO ring the reload of a stage (TMA round trip + statistics,
             // ~1400 cycles measured) starts when dV/dK of step i-1 complete; in program order S^T(i+1) -> dV/dK(i) the
             // issuer sat in the wait for that reload while P^T/dS^T of step i were already staged, which delayed the
@@ -567,29 +538,6 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     }
                 }
             }
-        } else {
-        for (int i = 0; i <= n_steps; ++i) {
-            if (i < n_steps) {
-                const int st = i % kB3Stages;
-                mbar_wait_backoff<32>(&qdo_full[st], (i / kB3Stages) & 1);
-                TAVK_TRACE(i, 2);
-                if (i >= 1) mbar_wait_backoff<32>(st_free, (i - 1) & 1);
-                TAVK_TRACE(i, 3);
-                tc_fence_after();
-                if (leader) issue_scores(i);
-                __syncwarp();
-                TAVK_TRACE(i, 4);
-            }
-            if (i >= 1) {
-                const int kstep = i - 1;
-                mbar_wait_backoff<32>(pds_full, kstep & 1);
-                TAVK_TRACE(kstep, 5);
-                tc_fence_after();
-                if (leader) issue_grads(kstep);
-                __syncwarp();
-                TAVK_TRACE(kstep, 6);
-            }
-        }
         }
         if (leader) umma_commit(done);
         __syncwarp();
@@ -598,13 +546,11 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int row = quarter * 32 + lane;                       // key row inside the tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int i = 0; i < n_steps; ++i) {
-            const int stg = i % kB3Stages;
-            if constexpr (!kAug) mbar_wait(&qdo_full[stg], (i / kB3Stages) & 1);   // the step's statistics are staged
             if (quarter == 0) TAVK_TRACE(i, 7);
             mbar_wait(st_full, i & 1);
             if (quarter == 0) TAVK_TRACE(i, 8);
             tc_fence_after();
-            if constexpr (kAug) {
+            {
                 // all 128 accumulator words of the row first, so the issuer can overwrite S^T / dP^T (step i+1) while
                 // this step's ex2 / products / stores run
                 uint32_t s0[32], s1[32], d0[32], d1[32];
@@ -639,51 +585,6 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 }
                 st_row_chunks(smem_u32(sP), row, 1, pk);
                 st_row_chunks(smem_u32(sDS), row, 1, dsk);
-            } else {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t s[32], dp[32];
-                tmem_ld_32x32(tmem_base + lane_sel + half * 32, s);
-                tmem_ld_32x32(tmem_base + lane_sel + 64 + half * 32, dp);
-                tmem_ld_wait();
-                if (half == 1) {   // S^T / dP^T of this step are in registers: the issuer may start step i+1
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(st_free);
-                    if (quarter == 0) TAVK_TRACE(i, 9);
-                }
-                uint32_t pk[16], dsk[16];
-                if constexpr (kAug) {
-                    // the statistics are already inside the accumulators: P^T = ex2(S^T c), dS^T = P^T dP^T
-#pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        const float p0 = ex2_approx(__uint_as_float(s[c]) * p.scale_log2);
-                        const float p1 = ex2_approx(__uint_as_float(s[c + 1]) * p.scale_log2);
-                        pk[c >> 1] = pack_bf16x2(p0, p1);
-                        dsk[c >> 1] = pack_bf16x2(p0 * __uint_as_float(dp[c]), p1 * __uint_as_float(dp[c + 1]));
-                    }
-                } else {
-                // per-query statistics of the 32 columns: broadcast LDS.128 from the producer's staging ring
-                const uint32_t st_addr = smem_u32(s_stats + stg * 128 + half * 32);
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 l4 = ld_shared_v4(st_addr + c * 4), d4 = ld_shared_v4(st_addr + 256 + c * 4);
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c]), p.scale_log2, -l4.x));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -l4.y));
-                    const float p2 = ex2_approx(fmaf(__uint_as_float(s[c + 2]), p.scale_log2, -l4.z));
-                    const float p3 = ex2_approx(fmaf(__uint_as_float(s[c + 3]), p.scale_log2, -l4.w));
-                    pk[c >> 1] = pack_bf16x2(p0, p1);
-                    pk[(c >> 1) + 1] = pack_bf16x2(p2, p3);
-                    dsk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[c]) - d4.x), p1 * (__uint_as_float(dp[c + 1]) - d4.y));
-                    dsk[(c >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[c + 2]) - d4.z), p3 * (__uint_as_float(dp[c + 3]) - d4.w));
-                }
-                }
-                if (half == 0 && quarter == 0) TAVK_TRACE(i, 10);
-                if (half == 0 && i >= 1) mbar_wait(pds_empty, (i - 1) & 1);   // dV/dK MMAs of step i-1 have read P^T/dS^T
-                if (half == 0 && quarter == 0) TAVK_TRACE(i, 11);
-                st_row_chunks(smem_u32(sP), row, half, pk);
-                st_row_chunks(smem_u32(sDS), row, half, dsk);
-            }
             }
             if (quarter == 0) TAVK_TRACE(i, 12);
             fence_proxy_async_smem();
@@ -727,7 +628,6 @@ attn_bwd_dkv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
-template <bool kTS>   // kTS: dS goes back into tensor memory and is the A operand of the dQ MMA from there (see the forward)
 __global__ void __launch_bounds__(kB3Threads, 2)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -739,8 +639,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     uint8_t* sDO = smem + kTcTile;
     uint8_t* sK = sDO + kTcTile;                      // ring
     uint8_t* sV = sK + kDq3Stages * kBwSmall;          // ring
-    uint8_t* sDS = sV + kDq3Stages * kBwSmall;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + kBwPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kDq3Stages * kBwSmall);
     uint64_t* qdo_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + kDq3Stages;
@@ -769,7 +668,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
     const uint32_t tmem_dq = tmem_base + 128;
-    const uint32_t tmem_ds = tmem_base + 192;          // kTS: bf16 dS, 32 columns
+    const uint32_t tmem_ds = tmem_base + 192;          // bf16 dS of the step, 32 columns
 
     if (warp_idx == 0) {
         if (lane == 0) {
@@ -790,7 +689,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         constexpr uint32_t idesc_mn = umma_idesc_bf16(128, kTcD, false, true);      // dQ (B = K_j MN-major)
         const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 16, 1024), dDO = umma_smem_desc(smem_u32(sDO), 16, 1024);
         const uint64_t dKk0 = umma_smem_desc(smem_u32(sK), 16, 1024), dVk0 = umma_smem_desc(smem_u32(sV), 16, 1024);
-        const uint64_t dKm0 = umma_smem_desc(smem_u32(sK), 8192, 1024), dDS0 = umma_smem_desc(smem_u32(sDS), 16, 1024);
+        const uint64_t dKm0 = umma_smem_desc(smem_u32(sK), 8192, 1024);
         mbar_wait(qdo_full, 0);
         tc_fence_after();
         for (int j = 0; j <= n_steps; ++j) {
@@ -817,12 +716,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                 if (leader) {
                     const uint64_t so = (uint64_t)(st * (kBwSmall >> 4));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if constexpr (kTS)
-                            umma_bf16_ts(tmem_dq, tmem_ds + (uint32_t)(k * 8), dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-                        else
-                            umma_bf16(tmem_dq, dDS0 + 2 * k, dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < 4; ++k)   // A = dS from tensor memory
+                        umma_bf16_ts(tmem_dq, tmem_ds + (uint32_t)(k * 8), dKm0 + so + (uint64_t)(k * 128), idesc_mn, (kstep > 0 || k > 0) ? 1u : 0u);
                     umma_commit(&kv_empty[st]);
                     umma_commit(ds_empty);
                 }
@@ -873,11 +768,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     }
                 }
                 if (half == 0 && j >= 1) mbar_wait(ds_empty, (j - 1) & 1);   // the dQ MMAs of step j-1 have read dS
-                if constexpr (kTS) tmem_st_32x16(tmem_ds + lane_sel + (uint32_t)(half * 16), dsk);
-                else st_row_chunks(smem_u32(sDS), row, half, dsk);
+                tmem_st_32x16(tmem_ds + lane_sel + (uint32_t)(half * 16), dsk);
             }
-            if constexpr (kTS) tmem_st_wait();
-            else fence_proxy_async_smem();
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
@@ -949,20 +842,12 @@ int attn_fwd_tc_launch(const tavk_attn_args* a, cudaStream_t stream) {
     d.B = a->B; d.S = a->S; d.nh = a->nh;
     d.scale_log2 = a->scale * kTcLog2e;
     static bool attr_done = false;
-    static bool ts = true;
     if (!attr_done) {
-        const char* e = getenv("TAVK_ATTN_TS");
-        ts = !(e != nullptr && e[0] == '0');
-        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3Smem));
         attr_done = true;
     }
     dim3 grid((a->S + kTcQ - 1) / kTcQ, a->nh, a->B);
-    if (ts) {
-        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel<true>, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
-    } else {
-        TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel<false>, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
-    }
+    TAVK_CUDA(launch_kernel(attn_fwd_tc64_kernel, dim3(grid), dim3(kF3Threads), (size_t)(kF3Smem), stream, tq, tk64, tv64, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1012,36 +897,14 @@ int attn_bwd_tc_launch(const tavk_attn_bwd_args* a, cudaStream_t stream) {
     d.scale = a->scale; d.scale_log2 = a->scale * kTcLog2e; d.inv_scale = 1.0f / a->scale;
     d.dbq = a->dbq; d.dbk = a->dbk; d.dbv = a->dbv;
     static bool attr_done = false;
-    static int aug = 3;
-    static bool ts = true;
     if (!attr_done) {
-        const char* e = getenv("TAVK_DKV_AUG");
-        if (e != nullptr && e[0] >= '0' && e[0] <= '3') aug = e[0] - '0';
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
-        const char* e2 = getenv("TAVK_ATTN_TS");
-        ts = !(e2 != nullptr && e2[0] == '0');
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
-        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkv3Smem));
+        TAVK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDq3Smem));
         attr_done = true;
     }
     dim3 grid((a->S + 127) / 128, a->nh, a->B);
-    if (aug == 3) {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<true, true>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-    } else if (aug == 2) {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<true, false>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-    } else if (aug == 1) {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<false, true>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-    } else {
-        TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel<false, false>, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
-    }
-    if (ts) {
-        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel<true>, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
-    } else {
-        TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel<false>, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
-    }
+    TAVK_CUDA(launch_kernel(attn_bwd_dkv_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDkv3Smem), stream, tq64, tk128, tv128, tdo64, d));
+    TAVK_CUDA(launch_kernel(attn_bwd_dq_tc2_kernel, dim3(grid), dim3(kB3Threads), (size_t)(kDq3Smem), stream, tq128, tk64, tv64, tdo128, d));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -3,8 +3,12 @@
 Builds a PRIVATE copy of the library with -DTAVK_ATTN_TRACE (multi-modal-emotion_b200/build/libtavk_trace.so; libtavk.so
 itself has the trace compiled out), runs one backward at B=16, S=1464 and dumps clock64() stamps of every hand-off of
 every step for 8 CTAs to gpurun_out/attn_trace_<variant>.json.
-  python tools/attn_trace.py build            # here (no GPU)
-  TAVK_DKV_AUG=2 python tools/attn_trace.py   # on the GPU box"""
+  python tools/attn_trace.py build     # here (no GPU)
+  python tools/attn_trace.py           # on the GPU box
+Slots per (cta, step): 0 producer passed qdo_empty, 1 producer arrived on qdo_full, 3 issuer about to issue S^T/dP^T,
+4 issued, 5 issuer saw pds_full, 6 dV/dK issued, 7 elementwise warp 2 starts waiting for st_full, 8 got it, 9 released
+S^T/dP^T (st_free), 10 first half computed, 11 passed pds_empty, 12 P^T/dS^T stored, 13 arrived on pds_full;
+row 63 of a CTA = (smid, start clock)."""
 import json
 import os
 import subprocess
@@ -55,8 +59,7 @@ def run():
         L.attn_bwd(q, k, v, o, do, lse, delta, dqkv[..., :H], dqkv[..., H:2 * H], dqkv[..., 2 * H:], B=B, S=S, nh=nh,
                    ld_qkv=3 * H, ld_o=H, ld_dqkv=3 * H)
         torch.cuda.synchronize()
-    tag = os.environ.get("TAVK_DKV_AUG", "default")
-    out = os.path.join(ROOT, "gpurun_out", "attn_trace_%s.json" % tag)
+    out = os.path.join(ROOT, "gpurun_out", "attn_trace_%s.json" % (sys.argv[1] if len(sys.argv) > 1 else "dkv"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     json.dump(buf.view(8, 64, 16).cpu().tolist(), open(out, "w"))
     print("wrote", out)
