@@ -5,6 +5,7 @@ itself has the trace compiled out), runs one backward at B=16, S=1464 and dumps 
 every step for 8 CTAs to gpurun_out/attn_trace_<variant>.json.
   python tools/attn_trace.py build     # here (no GPU)
   python tools/attn_trace.py           # on the GPU box
+  python tools/attn_trace.py summary gpurun_out/attn_trace_dkv.json
 Slots per (cta, step): 0 producer passed qdo_empty, 1 producer arrived on qdo_full, 3 issuer about to issue S^T/dP^T,
 4 issued, 5 issuer saw pds_full, 6 dV/dK issued, 7 elementwise warp 2 starts waiting for st_full, 8 got it, 9 released
 S^T/dP^T (st_free), 10 first half computed, 11 passed pds_empty, 12 P^T/dS^T stored, 13 arrived on pds_full;
@@ -65,5 +66,37 @@ def run():
     print("wrote", out)
 
 
+def summary(path, cta=2):
+    """Average phase durations (cycles) over steps 4..19 of one traced CTA."""
+    import statistics as st
+
+    t = json.load(open(path))
+    r = t[cta]
+    steps = range(4, 20)
+    avg = lambda f: st.mean(f(i) for i in steps)  # noqa: E731
+    print("%s: CTA %d on SM %d" % (path, cta, r[63][0]))
+    rows = [
+        ("period per step (st_full(i) -> st_full(i+1))", lambda i: r[i + 1][8] - r[i][8]),
+        ("elementwise: wait for S^T/dP^T (st_full)", lambda i: r[i][8] - r[i][7]),
+        ("elementwise: busy (st_full -> arrive pds_full)", lambda i: r[i][13] - r[i][8]),
+        ("  of which wait for pds_empty (dV/dK of step i-1 done)", lambda i: r[i][11] - r[i][10]),
+        ("  st_full -> S^T/dP^T released (st_free)", lambda i: r[i][9] - r[i][8]),
+        ("issuer: issue S^T/dP^T MMAs + commit", lambda i: r[i][4] - r[i][3]),
+        ("issuer: issue dV/dK MMAs + commits", lambda i: r[i][6] - r[i][5]),
+        ("issuer: P^T/dS^T staged -> noticed", lambda i: r[i][5] - r[i][13]),
+        ("S^T/dP^T issued -> visible to the elementwise warps", lambda i: r[i][8] - r[i][4]),
+        ("producer: stage free (qdo_empty) -> stage full (TMA issue + statistics + arrive)", lambda i: r[i][1] - r[i][0]),
+        ("dV/dK(i) issued -> producer sees the stage of step i+2 free", lambda i: r[i + 2][0] - r[i][6]),
+        ("S^T/dP^T released (i) -> S^T/dP^T of step i+1 being issued", lambda i: r[i + 1][3] - r[i][9]),
+    ]
+    for name, f in rows:
+        print("  %-85s %7.0f" % (name, avg(f)))
+
+
 if __name__ == "__main__":
-    build() if (len(sys.argv) > 1 and sys.argv[1] == "build") else run()
+    if len(sys.argv) > 1 and sys.argv[1] == "build":
+        build()
+    elif len(sys.argv) > 2 and sys.argv[1] == "summary":
+        summary(sys.argv[2])
+    else:
+        run()
