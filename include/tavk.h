@@ -239,6 +239,19 @@ int tavk_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
 int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sqnorm_dev, float max_norm, float grad_prescale,
                int zero_grad, void* stream);
+/* CUDA-graph-safe form of the same step (train_model/tav_train.py:61-63,148-149: AdamW's bias correction and the
+ * CosineAnnealingWarmRestarts learning rate both advance EVERY iteration, so neither may be a by-value kernel argument
+ * of a captured launch).  The optimiser clock lives in caller-owned device memory:
+ *   step_dev  int32[1]  number of completed steps;
+ *   hyper_dev f32[4]    {lr, 1-beta1^step, sqrt(1-beta2^step), unused}; the host writes hyper_dev[0] (the scheduler's
+ *                       current learning rate) before each step / graph replay.
+ * tavk_adamw_prep: ++*step_dev, recomputes hyper_dev[1..2] (double precision) and zeroes *sqnorm_dev (NULL allowed) —
+ * it takes the place of the memset in front of tavk_grad_sqnorm.  tavk_adamw_dev: tavk_adamw with lr and the bias
+ * corrections read from hyper_dev. */
+int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, float beta1, float beta2, void* stream);
+int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, const float* hyper_dev, float beta1,
+                   float beta2, float eps, float weight_decay, const float* sqnorm_dev, float max_norm,
+                   float grad_prescale, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

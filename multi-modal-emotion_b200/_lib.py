@@ -99,6 +99,8 @@ SIGNATURES = {
     "tavk_softmax_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_grad_sqnorm": [_P, _L, _P, _P],
     "tavk_adamw": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _F, _I, _P],
+    "tavk_adamw_prep": [_P, _P, _P, _F, _F, _P],
+    "tavk_adamw_dev": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _F, _F, _I, _P],
 }
 _RESTYPES = {"tavk_last_error": C.c_char_p}
 

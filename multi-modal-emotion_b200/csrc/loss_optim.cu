@@ -99,10 +99,31 @@ TAVK_DEVINL float adam_one(float& p, float& m, float& v, float g, const AdamArgs
     return p;
 }
 
+// Device-resident optimiser clock (tavk_adamw_prep): the step counter, the learning rate and the two bias corrections
+// live in device memory so that a captured CUDA graph advances them on every replay (by-value kernel arguments would
+// freeze the capture-time step and learning rate).  hyper = {lr, 1 - beta1^step, sqrt(1 - beta2^step), unused}.
+__global__ void adamw_prep_kernel(int* __restrict__ step, float* __restrict__ hyper, float* __restrict__ sqnorm,
+                                  float beta1, float beta2) {
+    pdl_wait();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int s = *step + 1;
+        *step = s;
+        hyper[1] = (float)(1.0 - pow((double)beta1, (double)s));
+        hyper[2] = (float)sqrt(1.0 - pow((double)beta2, (double)s));
+        if (sqnorm != nullptr) *sqnorm = 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float* __restrict__ g,
-             __nv_bfloat16* __restrict__ p_bf16, long long n, const float* __restrict__ sqnorm, AdamArgs a) {
+             __nv_bfloat16* __restrict__ p_bf16, long long n, const float* __restrict__ sqnorm,
+             const float* __restrict__ hyper, AdamArgs a) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
+    if (hyper != nullptr) {
+        a.lr = hyper[0];
+        a.bc1 = hyper[1];
+        a.bc2_sqrt = hyper[2];
+    }
     float gs = a.prescale;
     if (sqnorm != nullptr && a.max_norm > 0.f) {
         // clip_grad_norm_: the norm is taken over the (pre-scaled) gradient
@@ -194,7 +215,38 @@ extern "C" int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, 
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     TAVK_CUDA(launch_kernel(adamw_kernel, dim3((int)blocks), dim3(256), (size_t)(0), STREAM(stream), p, m, v, g, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
-                                                          sqnorm_dev, a));
+                                                          sqnorm_dev, (const float*)nullptr, a));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, float beta1, float beta2, void* stream) {
+    TAVK_CHECK(step_dev && hyper_dev, 1, "tavk_adamw_prep: null pointer");
+    TAVK_CHECK(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, 1, "tavk_adamw_prep: betas must be in [0,1)");
+    TAVK_CUDA(launch_kernel(adamw_prep_kernel, dim3(1), dim3(32), (size_t)(0), STREAM(stream), step_dev, hyper_dev, sqnorm_dev, beta1, beta2));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, const float* hyper_dev,
+                              float beta1, float beta2, float eps, float weight_decay, const float* sqnorm_dev,
+                              float max_norm, float grad_prescale, int zero_grad, void* stream) {
+    TAVK_CHECK(p && m && v && g && hyper_dev, 1, "tavk_adamw_dev: null pointer");
+    TAVK_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                 reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(hyper_dev)) & 15) == 0,
+               1, "tavk_adamw_dev: buffers must be 16-byte aligned");
+    TAVK_CHECK(p_bf16 == nullptr || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, 1,
+               "tavk_adamw_dev: bf16 shadow must be 8-byte aligned");
+    if (n <= 0) return 0;
+    AdamArgs a;
+    a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    a.bc1 = 1.f; a.bc2_sqrt = 1.f;      // replaced by hyper_dev[0..2] on the device
+    a.max_norm = max_norm; a.prescale = grad_prescale; a.zero_grad = zero_grad;
+    long long blocks = ((n + 3) / 4 + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    TAVK_CUDA(launch_kernel(adamw_kernel, dim3((int)blocks), dim3(256), (size_t)(0), STREAM(stream), p, m, v, g, reinterpret_cast<__nv_bfloat16*>(p_bf16), n,
+                                                          sqnorm_dev, hyper_dev, a));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

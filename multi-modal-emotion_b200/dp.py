@@ -122,8 +122,12 @@ class DataParallelTAV:
     normalisation, backward overlapped with bucketed gradient all-reduce, fused clip + AdamW on identical gradients."""
 
     def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=32, group=None,
-                 use_cuda_graph=False, graph_warmup=3):
+                 use_cuda_graph=False, graph_warmup=3, scheduler=None):
+        """``scheduler``: the reference's CosineAnnealingWarmRestarts (or any torch scheduler over ``optimizer``).
+        ``train_step(..., sched_t=epoch + i/iters)`` steps it after the update exactly like the reference loop
+        (train_model/tav_train.py:63); its learning rate reaches the captured graph through a device scalar."""
         self.model, self.pre, self.criterion, self.opt = model, PREFormer, criterion, optimizer
+        self.scheduler = scheduler
         self.clip, self.group, self.bucket_bytes = clip, group, bucket_mb << 20
         self.buckets = None
         self.use_cuda_graph, self.graph_warmup = use_cuda_graph, graph_warmup
@@ -162,20 +166,56 @@ class DataParallelTAV:
             st_lab.copy_(labels, non_blocking=True)
 
         load()
+        # Warm-up steps (allocator / lazy-initialisation effects, the flat parameter buffers of the first step) must not
+        # train: everything a step mutates is snapshotted here and put back after the capture, so the first replay is
+        # the first optimisation step on this batch (capture itself executes nothing).
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(self.graph_warmup):
+            for _ in range(max(1, self.graph_warmup)):
                 self._eager_step(st_in, st_lab, epoch, check)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = self._eager_step(st_in, st_lab, epoch, check)
+        self._restore(snap)
+        torch.cuda.synchronize()
         return {"graph": g, "inputs": st_in, "labels": st_lab, "loss": out}
 
-    def train_step(self, inputs, labels, epoch=1, check="train", next_batch=None):
+    def _stateful(self):
+        seen, out = set(), []
+        for m in (self.model, self.pre):
+            for t in list(m.parameters()) + list(m.buffers()):
+                if id(t) not in seen:
+                    seen.add(id(t))
+                    out.append(t)
+        return out
+
+    def _snapshot(self):
+        from . import engine
+
+        return {"tensors": [(t, t.detach().clone()) for t in self._stateful()], "opt": self.opt.snapshot(),
+                "dropout": {d: c.clone() for d, c in engine._dropout_counter.items()}}
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        from . import engine
+
+        for t, saved in snap["tensors"]:
+            t.data.copy_(saved)          # .data: parameters are views of the flat buffer by now; keep them views
+        self.opt.restore(snap["opt"])
+        for d, c in engine._dropout_counter.items():
+            if d in snap["dropout"]:
+                c.copy_(snap["dropout"][d])
+            else:
+                c.zero_()
+
+    def train_step(self, inputs, labels, epoch=1, check="train", next_batch=None, sched_t=None):
         """One optimisation step on this rank's shard.  Returns the GLOBAL loss as a device scalar.
+        ``sched_t``: when a scheduler was given, ``scheduler.step(sched_t)`` runs after the update (the reference's
+        ``scheduler.step(epoch + batch_idx / iters)``, train_model/tav_train.py:63).
 
         ``next_batch=(inputs, labels)`` (graph mode, host tensors): the batch the NEXT call will be given.  Its
         host-to-device copy is started on a copy stream into a staging set right after this step's graph launch, so it
@@ -183,7 +223,9 @@ class DataParallelTAV:
         synchronously, tav_train.py:15-40).  The next call recognises the batch by identity and only moves it
         device-to-device into the graph's static input buffers."""
         if not self.use_cuda_graph:
-            return self._eager_step(inputs, labels, epoch, check)
+            loss = self._eager_step(inputs, labels, epoch, check)
+            self._sched(sched_t)
+            return loss
         key = self._graph_key(inputs, labels, epoch, check)
         if self._graph is None or self._graph["key"] != key:
             self._graph = self._build_graph(inputs, labels, epoch, check)
@@ -207,10 +249,20 @@ class DataParallelTAV:
             if st["labels"].data_ptr() != labels.data_ptr():
                 st["labels"].copy_(labels, non_blocking=True)
         self._staged = None
+        self.opt.upload_lr()             # the scheduler's current learning rate -> the device scalar the graph reads
         st["graph"].replay()
+        self.opt.note_replayed()
+        self._sched(sched_t)
         if next_batch is not None:
             self._stage(next_batch[0], next_batch[1])
         return st["loss"]
+
+    def _sched(self, t):
+        if self.scheduler is not None:
+            if t is None:
+                self.scheduler.step()
+            else:
+                self.scheduler.step(t)
 
     @staticmethod
     def _same_batch(staged, inputs, labels):
@@ -248,7 +300,10 @@ class DataParallelTAV:
         """Device-resident input buffers of the captured step (write into them to skip the host copy)."""
         return (self._graph["inputs"], self._graph["labels"]) if self._graph else None
 
-    def _eager_step(self, inputs, labels, epoch=1, check="train"):
+    def _eager_step(self, inputs, labels, epoch=1, check="train", loss_scale=1.0, clip="default", Metric=None):
+        """forward + global loss + backward (+ bucketed all-reduce) + fused clip/AdamW.  ``loss_scale`` multiplies the
+        back-propagated loss (the reference's gradient-accumulation branch divides by ``accum_iter``,
+        train_model/tav_train.py:100); ``clip=None`` disables clipping for this step."""
         from .tav_train import get_statistics  # local import: tav_train imports optim, not dp
 
         crit = self.criterion
@@ -257,12 +312,12 @@ class DataParallelTAV:
         def parts_criterion(output, label, epoch=None):
             num, den = crit.parts(output, label, epoch)
             loss_bwd, loss_val = global_loss(num, den, self.group)
-            holder["value"] = loss_val
-            return loss_bwd
+            holder["value"] = loss_val * loss_scale if loss_scale != 1.0 else loss_val
+            return loss_bwd * loss_scale if loss_scale != 1.0 else loss_bwd
 
         if self.buckets is not None:
             self.buckets.start_backward()
-        loss = get_statistics(inputs, labels, self.model, self.pre, parts_criterion, None, check=check, epoch=epoch)
+        loss = get_statistics(inputs, labels, self.model, self.pre, parts_criterion, Metric, check=check, epoch=epoch)
         loss.backward()
         if self.world > 1:
             if self.buckets is not None:
@@ -272,5 +327,5 @@ class DataParallelTAV:
                 self.opt.materialize()
                 self.opt.flat.attach_grads()
                 dist.all_reduce(self.opt.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
-        self.opt.step(max_grad_norm=self.clip)
+        self.opt.step(max_grad_norm=self.clip if clip == "default" else clip)
         return holder["value"]

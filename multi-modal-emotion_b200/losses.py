@@ -16,15 +16,20 @@ class NewCrossEntropyLoss(nn.Module):
         super().__init__()
         self.class_weights = class_weights
         self.epoch_switch = epoch_switch
+        # Same child modules as the reference (utils/global_functions.py:63-64): they are state holders here (the
+        # fused kernel does the arithmetic), so ``state_dict()`` carries the reference's only key,
+        # ``weightedCEL.weight``, and a ``best.pt`` 'loss' entry loads in either direction.
+        self.weightedCEL = nn.CrossEntropyLoss(weight=class_weights)
+        self.normalCEL = nn.CrossEntropyLoss()
         self.iter1 = self.iter2 = self.iter3 = 1
 
     def _weights(self, epoch, device):
-        if epoch % self.epoch_switch == 0 or self.class_weights is None:
+        w = self.weightedCEL.weight
+        if epoch % self.epoch_switch == 0 or w is None:
             return None
-        w = self.class_weights
         if w.device != device or w.dtype != torch.float32:
             w = w.to(device=device, dtype=torch.float32)
-            self.class_weights = w
+            self.weightedCEL.weight = w            # re-registers the buffer on the compute device
         return w
 
     def parts(self, logits, target, epoch):

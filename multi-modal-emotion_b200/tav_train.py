@@ -4,8 +4,10 @@
 
 What changed underneath: inputs are moved to the device once; the B==1 assert on the video tensor
 (tav_train.py:32) is relaxed to a shape check so batched runs work; ``clip_grad_norm_`` + ``AdamW.step`` +
-``zero_grad`` are one fused step over flat buffers (optim.FusedAdamW); when ``torch.distributed`` is initialised the
-gradients are all-reduced in buckets overlapped with backward (dp.py).  Quirks kept on purpose: ``grad_accum`` steps
+``zero_grad`` are one fused step over flat buffers (optim.FusedAdamW); when ``torch.distributed`` is initialised with
+more than one rank, ``train_tav_network`` drives every training iteration through ``dp.DataParallelTAV`` (global-loss
+normalisation, bucketed gradient all-reduce overlapped with backward), so N ranks reproduce the single-process
+step on the concatenated batch instead of training N unsynchronised replicas.  Quirks kept on purpose: ``grad_accum`` steps
 the optimiser every iteration and once more at dialogue boundaries (Q10); the scheduler is stepped with the
 fractional epoch.  wandb logging and checkpoint files are host-side bookkeeping outside the hot path: logging goes
 through ``log_fn`` (defaults to wandb when it is importable and active, else a no-op) and checkpoints through
@@ -30,6 +32,7 @@ def _default_log(payload):
 
 
 log_fn = _default_log
+_dp_runner = None     # dp.DataParallelTAV while train_tav_network runs under torch.distributed (world_size > 1)
 checkpoint_io = None  # optional object with save(model, PREFormer, optimizer, criterion, scheduler, epoch, step) / load(...)
 
 
@@ -78,6 +81,15 @@ def _optimizer_step(model, PREFormer, optimizer, scheduler, clip, t):
         PREFormer.zero_grad()
 
 
+def _dp_step(train_input, train_label, Metric, epoch, loss_scale, clip, scheduler, t):
+    """One data-parallel iteration: forward on the local shard, GLOBAL loss, backward overlapped with the bucketed
+    all-reduce, fused clip + AdamW on identical gradients, scheduler step.  Returns the global loss as a float."""
+    loss = _dp_runner._eager_step(train_input, train_label, epoch, "train", loss_scale=loss_scale, clip=clip,
+                                  Metric=Metric)     # Metric accumulates this rank's shard
+    scheduler.step(t)
+    return loss.item()
+
+
 def _validate_and_track(epoch, batch_idx, val_dataloader, model, PREFormer, criterion, optimizer, scheduler, Metric,
                         prev_val_loss, total_loss_train, iters, patience):
     global PATIENCE_ITER
@@ -96,10 +108,13 @@ def _validate_and_track(epoch, batch_idx, val_dataloader, model, PREFormer, crit
 def not_grad_accum(epoch, train_dataloader, val_dataloader, model, PREFormer, criterion, optimizer, scheduler, clip,
                    patience, Metric, prev_val_loss, total_loss_train, iters, log_val, path):
     for batch_idx, (train_input, train_label) in enumerate(train_dataloader):
-        loss = get_statistics(train_input, train_label, model, PREFormer, criterion, Metric, check="train", epoch=epoch)
-        total_loss_train += loss.item()
-        loss.backward()
-        _optimizer_step(model, PREFormer, optimizer, scheduler, clip, epoch + batch_idx / iters)
+        if _dp_runner is not None:
+            total_loss_train += _dp_step(train_input, train_label, Metric, epoch, 1.0, clip, scheduler, epoch + batch_idx / iters)
+        else:
+            loss = get_statistics(train_input, train_label, model, PREFormer, criterion, Metric, check="train", epoch=epoch)
+            total_loss_train += loss.item()
+            loss.backward()
+            _optimizer_step(model, PREFormer, optimizer, scheduler, clip, epoch + batch_idx / iters)
         if ((batch_idx + 1) % log_val == 0) or (batch_idx + 1 == iters):
             prev_val_loss, stop = _validate_and_track(epoch, batch_idx, val_dataloader, model, PREFormer, criterion,
                                                       optimizer, scheduler, Metric, prev_val_loss, total_loss_train,
@@ -113,10 +128,14 @@ def grad_accum(epoch, train_dataloader, val_dataloader, model, PREFormer, criter
                patience, Metric, prev_val_loss, total_loss_train, iters, log_val, path):
     for batch_idx, (train_input, train_label) in enumerate(train_dataloader):
         accum_iter, accum_sum = train_dataloader.dataset.retGradAccum(i=batch_idx)
-        loss = get_statistics(train_input, train_label, model, PREFormer, criterion, Metric, check="train", epoch=epoch) / accum_iter
-        total_loss_train += loss.item()
-        loss.backward()
-        _optimizer_step(model, PREFormer, optimizer, scheduler, clip, epoch + batch_idx / iters)
+        if _dp_runner is not None:
+            total_loss_train += _dp_step(train_input, train_label, Metric, epoch, 1.0 / accum_iter, clip, scheduler,
+                                         epoch + batch_idx / iters)
+        else:
+            loss = get_statistics(train_input, train_label, model, PREFormer, criterion, Metric, check="train", epoch=epoch) / accum_iter
+            total_loss_train += loss.item()
+            loss.backward()
+            _optimizer_step(model, PREFormer, optimizer, scheduler, clip, epoch + batch_idx / iters)
         if ((batch_idx + 1) % accum_sum == 0) or (batch_idx + 1 == iters):   # second step at dialogue boundaries (Q10)
             _optimizer_step(model, PREFormer, optimizer, scheduler, None, epoch + batch_idx / iters)
         if ((batch_idx + 1) % log_val == 0) or (batch_idx + 1 == iters):
@@ -152,7 +171,9 @@ def one_epoch(epoch, train_dataloader, val_dataloader, model, PREFormer, criteri
 
 def train_tav_network(model, PREFormer, train_dataloader, val_dataloader, criterion, learning_rate, epochs,
                       weight_decay, T_max, Metric, patience, clip, epoch_switch, checkpoint=None):
-    global PATIENCE_ITER
+    global PATIENCE_ITER, _dp_runner
+    from . import dp
+
     PATIENCE_ITER = 0
     params = [p for p in model.parameters() if p.requires_grad] + [p for p in PREFormer.parameters() if p.requires_grad]
     optimizer = FusedAdamW(params, lr=learning_rate, weight_decay=weight_decay)
@@ -161,14 +182,19 @@ def train_tav_network(model, PREFormer, train_dataloader, val_dataloader, criter
     if checkpoint is not None:
         optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
         scheduler.load_state_dict(checkpoint["scheduler_state_dict"])
-    for epoch_num in range(epochs):
-        log_fn({"epoch": epoch_num, "learning_rate": scheduler.get_last_lr()[0]})
-        optimizer.zero_grad()
-        model, PREFormer, optimizer, criterion, scheduler, prev_val_loss = one_epoch(
-            epoch_num, train_dataloader, val_dataloader, model, PREFormer, criterion, optimizer, scheduler, clip,
-            epoch_switch, patience, Metric, prev_val_loss)
-        if PATIENCE_ITER == patience:
-            return model, PREFormer
+    # under torchrun every rank holds a shard of each batch: couple the replicas
+    _dp_runner = dp.DataParallelTAV(model, PREFormer, criterion, optimizer, clip=clip) if dp.is_distributed() else None
+    try:
+        for epoch_num in range(epochs):
+            log_fn({"epoch": epoch_num, "learning_rate": scheduler.get_last_lr()[0]})
+            optimizer.zero_grad()
+            model, PREFormer, optimizer, criterion, scheduler, prev_val_loss = one_epoch(
+                epoch_num, train_dataloader, val_dataloader, model, PREFormer, criterion, optimizer, scheduler, clip,
+                epoch_switch, patience, Metric, prev_val_loss)
+            if PATIENCE_ITER == patience:
+                return model, PREFormer
+    finally:
+        _dp_runner = None
     return model, PREFormer
 
 

@@ -162,3 +162,26 @@ def test_video_patch_cache_never_serves_a_recycled_address():
     cc = frontends.video_patches_bf16(c, 2, 16)
     c.add_(1.0)                                                          # in-place write: version counter moves
     assert torch.equal(frontends.video_patches_bf16(c, 2, 16), ref(c))
+
+
+def test_criterion_state_dict_carries_the_reference_key_both_directions():
+    """The reference criterion owns nn.CrossEntropyLoss(weight=...) as ``weightedCEL`` (utils/global_functions.py:63), so
+    best.pt's 'loss' entry is {'weightedCEL.weight': ...}; ours must emit and accept exactly that."""
+    import torch
+    from torch import nn
+
+    from multi_modal_emotion_b200.losses import NewCrossEntropyLoss
+
+    class ReferenceShaped(nn.Module):          # the reference's module tree, state-wise
+        def __init__(self, w):
+            super().__init__()
+            self.weightedCEL = nn.CrossEntropyLoss(weight=w)
+            self.normalCEL = nn.CrossEntropyLoss()
+
+    w = torch.tensor([0.5, 0.9, 1.0])
+    ours, ref = NewCrossEntropyLoss(w.clone(), epoch_switch=2), ReferenceShaped(w.clone() * 2)
+    assert list(ours.state_dict()) == list(ref.state_dict()) == ["weightedCEL.weight"]
+    ours.load_state_dict(ref.state_dict())
+    assert torch.equal(ours.weightedCEL.weight, w * 2)
+    ref.load_state_dict(NewCrossEntropyLoss(w.clone()).state_dict())
+    assert torch.equal(ref.weightedCEL.weight, w)
