@@ -30,7 +30,10 @@ enum { TAVK_F32 = 0, TAVK_BF16 = 1 };
 enum {
     TAVK_EPI_LINEAR = 0,   /* out = alpha*acc (+bias) (+rowbias) (+resid)                               */
     TAVK_EPI_GELU = 1,     /* out = bf16(pre), out2 = bf16(gelu_erf(pre)), pre = alpha*acc + bias      */
-    TAVK_EPI_GELU_BWD = 2  /* out = bf16((alpha*acc + bias) * gelu_erf'(aux)); bf16 output only             */
+    TAVK_EPI_GELU_BWD = 2, /* out = bf16((alpha*acc + bias) * gelu_erf'(aux)); bf16 output only             */
+    TAVK_EPI_GELU_GRAD = 3,/* out = bf16(gelu_erf'(pre)), out2 = bf16(gelu_erf(pre)): the forward saves the derivative
+                              instead of the pre-activation ...                                              */
+    TAVK_EPI_MUL = 4       /* ... so that the backward is out = bf16((alpha*acc + bias) * aux), aux = that derivative */
 };
 
 /* attention mask modes */
@@ -248,9 +251,9 @@ int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, 
  * tavk_adamw_prep: ++*step_dev, recomputes hyper_dev[1..2] (double precision) and zeroes *sqnorm_dev (NULL allowed) —
  * it takes the place of the memset in front of tavk_grad_sqnorm.  tavk_adamw_dev: tavk_adamw with lr and the bias
  * corrections read from hyper_dev. */
-int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, float beta1, float beta2, void* stream);
-int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, const float* hyper_dev, float beta1,
-                   float beta2, float eps, float weight_decay, const float* sqnorm_dev, float max_norm,
+int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, double beta1, double beta2, void* stream);
+int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, const float* hyper_dev, double beta1,
+                   double beta2, float eps, float weight_decay, const float* sqnorm_dev, float max_norm,
                    float grad_prescale, int zero_grad, void* stream);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtavk.so")
 
 F32, BF16 = 0, 1
-EPI_LINEAR, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
+EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2, 3, 4
 ATTN_NONE, ATTN_KEY_BIAS = 0, 1
 
 
@@ -99,8 +99,8 @@ SIGNATURES = {
     "tavk_softmax_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_grad_sqnorm": [_P, _L, _P, _P],
     "tavk_adamw": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _F, _I, _P],
-    "tavk_adamw_prep": [_P, _P, _P, _F, _F, _P],
-    "tavk_adamw_dev": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _F, _F, _I, _P],
+    "tavk_adamw_prep": [_P, _P, _P, C.c_double, C.c_double, _P],
+    "tavk_adamw_dev": [_P, _P, _P, _P, _P, _L, _P, C.c_double, C.c_double, _F, _F, _P, _F, _F, _I, _P],
 }
 _RESTYPES = {"tavk_last_error": C.c_char_p}
 

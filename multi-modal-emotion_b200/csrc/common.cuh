@@ -182,6 +182,27 @@ TAVK_DEVINL void gelu_grad_mul2(float x0, float x1, float& v0, float& v1) {
     const f32x2 g = fma2(mul2(x, pk(0.3989422804f, 0.3989422804f)), e, cdf);
     unpk(mul2(pk(v0, v1), g), v0, v1);
 }
+// gelu(x) AND gelu'(x) from one evaluation of the A&S 7.1.26 form above: g = x Phi(x), d = Phi(x) + x phi(x).  The FFN-up
+// forward stores d (bf16) instead of the pre-activation, which turns the backward's GELU' epilogue into one multiply.
+TAVK_DEVINL void gelu_and_grad2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+    const f32x2 x = pk(x0, x1), ax = pk(fabsf(x0), fabsf(x1));
+    float t0, t1;
+    unpk(fma2(ax, pk(2.316418883e-01f, 2.316418883e-01f), pk(1.0f, 1.0f)), t0, t1);
+    const f32x2 t = pk(rcp_approx(t0), rcp_approx(t1));
+    f32x2 q = fma2(t, pk(1.061405429f, 1.061405429f), pk(-1.453152027f, -1.453152027f));
+    q = fma2(q, t, pk(1.421413741f, 1.421413741f));
+    q = fma2(q, t, pk(-0.284496736f, -0.284496736f));
+    q = fma2(q, t, pk(0.254829592f, 0.254829592f));
+    q = mul2(q, t);
+    float e0, e1;
+    unpk(mul2(mul2(x, x), pk(-0.72134752f, -0.72134752f)), e0, e1);   // -x^2/2 * log2(e)
+    const f32x2 e = pk(ex2_approx(e0), ex2_approx(e1));
+    float h0, h1;
+    unpk(fma2(mul2(q, e), pk(-0.5f, -0.5f), pk(0.5f, 0.5f)), h0, h1);
+    const f32x2 cdf = add2(pk(copysignf(h0, x0), copysignf(h1, x1)), pk(0.5f, 0.5f));
+    unpk(mul2(x, cdf), g0, g1);
+    unpk(fma2(mul2(x, pk(0.3989422804f, 0.3989422804f)), e, cdf), d0, d1);
+}
 TAVK_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -84,7 +84,7 @@ template <int MODE>
 struct EpiOperands {        // what one chunk needs from global memory besides the accumulator
     float4 b4;
     float4 res[MODE == TAVK_EPI_LINEAR ? 8 : 1];
-    uint2 aux[MODE == TAVK_EPI_GELU_BWD ? 8 : 1];
+    uint2 aux[(MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL) ? 8 : 1];
 };
 
 template <int MODE>
@@ -113,7 +113,7 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
             }
         }
     }
-    if (MODE == TAVK_EPI_GELU_BWD) {
+    if (MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL) {
         const __nv_bfloat16* ap = p.aux + (long long)(w.row_base + rsub) * p.ldaux + w.col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -147,7 +147,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
     const long long ostep = 4 * p.ldo * kEsz;
     char* op2 = nullptr;
     long long ostep2 = 0;
-    if (MODE == TAVK_EPI_GELU) {
+    if (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD) {
         op2 = reinterpret_cast<char*>(p.out2) + ((long long)(w.row_base + rsub) * p.ldo2 + w.col) * 2;
         ostep2 = 4 * p.ldo2 * 2;
     }
@@ -160,11 +160,18 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
         float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
         unpk(fma2(pk(v.x, v.y), alpha2, blo), v.x, v.y);
         unpk(fma2(pk(v.z, v.w), alpha2, bhi), v.z, v.w);
-        if (MODE == TAVK_EPI_GELU) {
-            // out = pre-activation (bf16), out2 = GELU(pre) (bf16)
+        if (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD) {
+            // out = pre-activation (GELU) or gelu'(pre) (GELU_GRAD), out2 = gelu(pre); all bf16
             float4 g;
-            gelu_fast2(v.x, v.y, g.x, g.y);
-            gelu_fast2(v.z, v.w, g.z, g.w);
+            if (MODE == TAVK_EPI_GELU) {
+                gelu_fast2(v.x, v.y, g.x, g.y);
+                gelu_fast2(v.z, v.w, g.z, g.w);
+            } else {
+                float4 dgl;
+                gelu_and_grad2(v.x, v.y, g.x, g.y, dgl.x, dgl.y);
+                gelu_and_grad2(v.z, v.w, g.z, g.w, dgl.z, dgl.w);
+                v = dgl;
+            }
             uint2 a, gg;
             a.x = pack_bf16x2(v.x, v.y);  a.y = pack_bf16x2(v.z, v.w);
             gg.x = pack_bf16x2(g.x, g.y); gg.y = pack_bf16x2(g.z, g.w);
@@ -179,6 +186,9 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
                 const float2 a0 = unpack_bf16x2(o.aux[i].x), a1 = unpack_bf16x2(o.aux[i].y);
                 gelu_grad_mul2(a0.x, a0.y, v.x, v.y);
                 gelu_grad_mul2(a1.x, a1.y, v.z, v.w);
+            } else if (MODE == TAVK_EPI_MUL) {
+                const float2 a0 = unpack_bf16x2(o.aux[i].x), a1 = unpack_bf16x2(o.aux[i].y);
+                v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
             } else {
                 v.x += o.res[i].x; v.y += o.res[i].y; v.z += o.res[i].z; v.w += o.res[i].w;
             }
@@ -202,7 +212,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
         }
         op += ostep;
     }
-    if (MODE != TAVK_EPI_GELU && p.colsum != nullptr) {
+    if (MODE != TAVK_EPI_GELU && MODE != TAVK_EPI_GELU_GRAD && p.colsum != nullptr) {
         // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
         float cs0, cs1, cs2, cs3;
         unpk(cslo, cs0, cs1);
@@ -405,6 +415,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #define TAVK_EPI(MODE, OUT) \
     epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
         if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI(TAVK_EPI_GELU, OUT_BF16);
+        else if (p.epilogue == TAVK_EPI_GELU_GRAD) TAVK_EPI(TAVK_EPI_GELU_GRAD, OUT_BF16);
+        else if (p.epilogue == TAVK_EPI_MUL) TAVK_EPI(TAVK_EPI_MUL, OUT_BF16);
         else if (p.epilogue == TAVK_EPI_GELU_BWD) TAVK_EPI(TAVK_EPI_GELU_BWD, OUT_BF16);
         else if (p.out_bf16) TAVK_EPI(TAVK_EPI_LINEAR, OUT_BF16);
         else if (p.accumulate) TAVK_EPI(TAVK_EPI_LINEAR, OUT_RED);
@@ -486,10 +498,13 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     TAVK_CHECK(!(a->accumulate || k_splits > 1) || a->out_dtype == TAVK_F32, 1,
                "tavk_gemm_bf16: accumulate / split-K need an f32 output");
     TAVK_CHECK(k_splits == 1 || a->accumulate, 1, "tavk_gemm_bf16: split-K requires accumulate=1 (atomic adds)");
-    TAVK_CHECK(a->epilogue != TAVK_EPI_GELU || (a->out_dtype == TAVK_BF16 && a->out2 != nullptr && k_splits == 1), 1,
-               "tavk_gemm_bf16: GELU epilogue needs bf16 out + out2 and no split-K");
-    TAVK_CHECK(a->epilogue != TAVK_EPI_GELU_BWD || (a->aux != nullptr && k_splits == 1 && a->out_dtype == TAVK_BF16), 1,
-               "tavk_gemm_bf16: GELU_BWD epilogue needs aux, a bf16 output and no split-K");
+    TAVK_CHECK(a->epilogue >= TAVK_EPI_LINEAR && a->epilogue <= TAVK_EPI_MUL, 1, "tavk_gemm_bf16: bad epilogue %d", a->epilogue);
+    const bool epi_gelu = a->epilogue == TAVK_EPI_GELU || a->epilogue == TAVK_EPI_GELU_GRAD;
+    const bool epi_aux = a->epilogue == TAVK_EPI_GELU_BWD || a->epilogue == TAVK_EPI_MUL;
+    TAVK_CHECK(!epi_gelu || (a->out_dtype == TAVK_BF16 && a->out2 != nullptr && k_splits == 1), 1,
+               "tavk_gemm_bf16: GELU / GELU_GRAD epilogues need bf16 out + out2 and no split-K");
+    TAVK_CHECK(!epi_aux || (a->aux != nullptr && k_splits == 1 && a->out_dtype == TAVK_BF16), 1,
+               "tavk_gemm_bf16: GELU_BWD / MUL epilogues need aux, a bf16 output and no split-K");
     TAVK_CHECK(a->rowbias == nullptr || a->rows_per_group > 0, 1, "tavk_gemm_bf16: rowbias needs rows_per_group");
     const int vec = (a->out_dtype == TAVK_BF16) ? 8 : 4;
     TAVK_CHECK(a->ldo % vec == 0, 1, "tavk_gemm_bf16: ldo must be a multiple of %d", vec);

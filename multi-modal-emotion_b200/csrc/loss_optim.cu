@@ -86,14 +86,14 @@ grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__
 // ---------------------------------------------------------------- AdamW
 // Same update order as torch.optim.AdamW (single-tensor path): decay, moments, bias-corrected step.
 struct AdamArgs {
-    float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm, prescale;
+    float lr, beta1, beta2, omb1, omb2, eps, wd, bc1, bc2_sqrt, max_norm, prescale;   // omb = 1 - beta, rounded from double
     int zero_grad;
 };
 
 TAVK_DEVINL float adam_one(float& p, float& m, float& v, float g, const AdamArgs& a) {
     p *= (1.0f - a.lr * a.wd);
-    m = a.beta1 * m + (1.0f - a.beta1) * g;
-    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
+    m = a.beta1 * m + a.omb1 * g;
+    v = a.beta2 * v + a.omb2 * g * g;
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     p -= (a.lr / a.bc1) * (m / denom);
     return p;
@@ -103,13 +103,13 @@ TAVK_DEVINL float adam_one(float& p, float& m, float& v, float g, const AdamArgs
 // live in device memory so that a captured CUDA graph advances them on every replay (by-value kernel arguments would
 // freeze the capture-time step and learning rate).  hyper = {lr, 1 - beta1^step, sqrt(1 - beta2^step), unused}.
 __global__ void adamw_prep_kernel(int* __restrict__ step, float* __restrict__ hyper, float* __restrict__ sqnorm,
-                                  float beta1, float beta2) {
+                                  double beta1, double beta2) {
     pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int s = *step + 1;
         *step = s;
-        hyper[1] = (float)(1.0 - pow((double)beta1, (double)s));
-        hyper[2] = (float)sqrt(1.0 - pow((double)beta2, (double)s));
+        hyper[1] = (float)(1.0 - pow(beta1, (double)s));
+        hyper[2] = (float)sqrt(1.0 - pow(beta2, (double)s));
         if (sqnorm != nullptr) *sqnorm = 0.f;
     }
 }
@@ -208,6 +208,7 @@ extern "C" int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, 
     if (n <= 0) return 0;
     AdamArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    a.omb1 = 1.0f - beta1; a.omb2 = 1.0f - beta2;
     a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.max_norm = max_norm; a.prescale = grad_prescale; a.zero_grad = zero_grad;
@@ -220,7 +221,7 @@ extern "C" int tavk_adamw(float* p, float* m, float* v, float* g, void* p_bf16, 
     return 0;
 }
 
-extern "C" int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, float beta1, float beta2, void* stream) {
+extern "C" int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_dev, double beta1, double beta2, void* stream) {
     TAVK_CHECK(step_dev && hyper_dev, 1, "tavk_adamw_prep: null pointer");
     TAVK_CHECK(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, 1, "tavk_adamw_prep: betas must be in [0,1)");
     TAVK_CUDA(launch_kernel(adamw_prep_kernel, dim3(1), dim3(32), (size_t)(0), STREAM(stream), step_dev, hyper_dev, sqnorm_dev, beta1, beta2));
@@ -229,7 +230,7 @@ extern "C" int tavk_adamw_prep(int* step_dev, float* hyper_dev, float* sqnorm_de
 }
 
 extern "C" int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf16, int64_t n, const float* hyper_dev,
-                              float beta1, float beta2, float eps, float weight_decay, const float* sqnorm_dev,
+                              double beta1, double beta2, float eps, float weight_decay, const float* sqnorm_dev,
                               float max_norm, float grad_prescale, int zero_grad, void* stream) {
     TAVK_CHECK(p && m && v && g && hyper_dev, 1, "tavk_adamw_dev: null pointer");
     TAVK_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
@@ -239,7 +240,10 @@ extern "C" int tavk_adamw_dev(float* p, float* m, float* v, float* g, void* p_bf
                "tavk_adamw_dev: bf16 shadow must be 8-byte aligned");
     if (n <= 0) return 0;
     AdamArgs a;
-    a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    // betas arrive as doubles so that 1 - beta is rounded once, like torch's Python-scalar arithmetic (1 - 0.999 taken in
+    // float is 1.3e-5 off in relative terms, which shows in exp_avg_sq)
+    a.lr = 0.f; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = eps; a.wd = weight_decay;
+    a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
     a.bc1 = 1.f; a.bc2_sqrt = 1.f;      // replaced by hyper_dev[0..2] on the device
     a.max_norm = max_norm; a.prescale = grad_prescale; a.zero_grad = zero_grad;
     long long blocks = ((n + 3) / 4 + 255) / 256;

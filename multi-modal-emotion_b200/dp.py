@@ -52,6 +52,7 @@ class GradBuckets:
             i = j - 1
         del ends
         self.pending = [0] * len(self.buckets)
+        self.streams = [set() for _ in self.buckets]
         self.works = []
         self.enabled = False
         self.cuda = flat.grad.is_cuda
@@ -64,6 +65,7 @@ class GradBuckets:
         from . import engine
 
         self.pending = [n for (_, _, n) in self.buckets]
+        self.streams = [set() for _ in self.buckets]    # streams that wrote gradients of each bucket (tav.branch_streams)
         self.works = []
         self.enabled = True
         self.launched = 0
@@ -81,6 +83,8 @@ class GradBuckets:
         view = self.flat.grad[s:e]
         if self.cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            for st in self.streams[b]:
+                self.comm_stream.wait_stream(st)     # a bucket may hold parameters of several concurrently running branches
             with torch.cuda.stream(self.comm_stream):
                 self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
@@ -91,6 +95,8 @@ class GradBuckets:
         if not self.enabled:
             return
         b = self.param_bucket[id(p)]
+        if self.cuda:
+            self.streams[b].add(torch.cuda.current_stream())
         self.pending[b] -= 1
         if self.pending[b] == 0:
             self._launch(b)

@@ -215,8 +215,10 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
         x1 = _f32((M, H), dev)
         L.gemm(o, sh.wo, x1, M=M, N=H, K=H, bias=d["bo"], resid=x, rowbias=rb, rows_per_group=S)
         h2, _, mean2, rstd2 = L.layernorm_fwd(x1, d["ln2_w"], d["ln2_b"], spec.eps)
+        # `pre` receives gelu'(pre-activation) when a backward will follow (EPI_GELU_GRAD): the backward's dgrad GEMM then
+        # only multiplies by it (EPI_MUL) instead of evaluating the GELU derivative in its (issue-bound) epilogue
         pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
-        L.gemm(h2, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU)
+        L.gemm(h2, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
         y = _f32((M, H), dev)
         L.gemm(act, sh.w2, y, M=M, N=H, K=I, bias=d["b2"], resid=x1)
         if keep:
@@ -237,7 +239,7 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
     L.gemm(o_used, sh.wo, a, M=M, N=H, K=H, bias=d["bo"], resid=x)
     y_bf, y_f32, mean1, rstd1 = L.layernorm_fwd(a, d["ln1_w"], d["ln1_b"], spec.eps, want_bf16=True, want_f32=True)
     pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
-    L.gemm(y_bf, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU)
+    L.gemm(y_bf, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
     f = _f32((M, H), dev)
     L.gemm(act, sh.w2, f, M=M, N=H, K=I, bias=d["b2"], resid=y_f32)
     z_bf, z_f32, mean2, rstd2 = L.layernorm_fwd(f, d["ln2_w"], d["ln2_b"], spec.eps, want_bf16=True, want_f32=True)
@@ -323,7 +325,7 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
         _wgrad(dy_bf, sv.act, H, I, M, out=go.target("w2"))
         dpre = _bf16((M, I), dev)
         # the GELU' dgrad GEMM also accumulates the column sums of dpre (= b1 gradient) in its epilogue
-        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=go.target("b1"))
+        L.gemm(dy_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_MUL, colsum=go.target("b1"))
         # FFN up
         _wgrad(dpre, sv.h2, I, H, M, out=go.target("w1"))
         dh2 = _f32((M, H), dev)
@@ -352,7 +354,7 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
                                     want_f32=True, want_bf16=True, dx_colsum=go.target("b2"))
         _wgrad(df_bf, sv.act, H, I, M, out=go.target("w2"))
         dpre = _bf16((M, I), dev)
-        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_GELU_BWD, colsum=go.target("b1"))
+        L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_MUL, colsum=go.target("b1"))
         _wgrad(dpre, sv.h2, I, H, M, out=go.target("w1"))
         dyl = _f32((M, H), dev)
         L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)

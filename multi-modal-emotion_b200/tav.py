@@ -19,6 +19,21 @@ from .tavformer import VideoMAEEncoder
 _VARIANT = "reference"
 _FP16_MIN = torch.finfo(torch.float16).min
 
+# TAVForMAE.forward runs its four independent sub-graphs — Wav2Vec2, VideoMAE, RoBERTa and the fusion encoder, which
+# only meet at the final concat (reference models/tav.py:476-495) — on four CUDA streams.  Three of them have few rows
+# (B*149, B*70, B*323 against VideoMAE's B*1464): alone their kernels leave most of the 148 SMs idle, together they
+# fill them.  Autograd replays each sub-graph's backward on its forward stream, so the backward overlaps the same way,
+# and a CUDA-graph capture records the fork/join as graph dependencies.
+branch_streams = True
+_BRANCH_STREAMS = {}
+
+
+def _side_streams(dev):
+    st = _BRANCH_STREAMS.get(dev)
+    if st is None:
+        st = _BRANCH_STREAMS[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+    return st
+
 
 def set_encoder_variant(name):
     """"reference" | "baseline" | "tiny" | "tiny_base" — sizes of the three HF encoders built by the next constructors
@@ -229,17 +244,49 @@ class TAVForMAE(nn.Module):
         keep_count = getattr(self, "static_keep_count", None)
         if visual_mask is not None and not visual_mask.is_cuda:
             keep_count = int((~visual_mask[0]).sum())
-        to = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
-        av = engine.embed_add(to(hidden_states), to(pos_embed), self.embedding.weight)                 # :474
-        aud = hf.run_wav2vec2(self.wav2vec2, to(audio_features))                                        # :476
-        aud = engine.mean_pool(engine.linear_bf16(aud, self.wav_2_768_2.weight, self.wav_2_768_2.bias))  # :478
-        vid = engine.mean_pool(hf.run_videomae(self.videomae, to(video_embeds), to(visual_mask), keep_count))  # :480-481
-        _, t = hf.run_roberta(self.bert, to(input_ids), to(text_attention_mask))                        # :485
-        t = engine.layer_norm(t, self.bert_norm.weight, self.bert_norm.bias, self.bert_norm.eps)        # :486
-        av = self.random_mae_encoder(av, to(attention_mask))                                            # :487
-        av = engine.layer_norm(engine.mean_pool(av), self.rand_norm.weight, self.rand_norm.bias, self.rand_norm.eps)
-        aud = engine.layer_norm(aud, self.aud_norm.weight, self.aud_norm.bias, self.aud_norm.eps)       # :489
-        vid = engine.layer_norm(vid, self.vid_norm.weight, self.vid_norm.bias, self.vid_norm.eps)       # :490
+        to = lambda t: None if t is None else t.to(dev, non_blocking=True)  # noqa: E731
+        hidden_states, pos_embed, attention_mask = to(hidden_states), to(pos_embed), to(attention_mask)
+        audio_features, video_embeds, visual_mask = to(audio_features), to(video_embeds), to(visual_mask)
+        input_ids, text_attention_mask = to(input_ids), to(text_attention_mask)
+
+        def audio_branch():
+            aud = hf.run_wav2vec2(self.wav2vec2, audio_features)                                        # :476
+            aud = engine.mean_pool(engine.linear_bf16(aud, self.wav_2_768_2.weight, self.wav_2_768_2.bias))  # :478
+            return engine.layer_norm(aud, self.aud_norm.weight, self.aud_norm.bias, self.aud_norm.eps)  # :489
+
+        def video_branch():
+            vid = engine.mean_pool(hf.run_videomae(self.videomae, video_embeds, visual_mask, keep_count))  # :480-481
+            return engine.layer_norm(vid, self.vid_norm.weight, self.vid_norm.bias, self.vid_norm.eps)  # :490
+
+        def text_branch():
+            _, t = hf.run_roberta(self.bert, input_ids, text_attention_mask)                            # :485
+            return engine.layer_norm(t, self.bert_norm.weight, self.bert_norm.bias, self.bert_norm.eps)  # :486
+
+        def fusion_branch():
+            av = engine.embed_add(hidden_states, pos_embed, self.embedding.weight)                      # :474
+            av = self.random_mae_encoder(av, attention_mask)                                            # :487
+            return engine.layer_norm(engine.mean_pool(av), self.rand_norm.weight, self.rand_norm.bias, self.rand_norm.eps)
+
+        if branch_streams:
+            main = torch.cuda.current_stream(dev)
+            side = _side_streams(dev)
+            work = ((audio_branch, (audio_features,)), (text_branch, (input_ids, text_attention_mask)),
+                    (fusion_branch, (hidden_states, pos_embed, attention_mask)))
+            outs = []
+            for s_, (fn, ins) in zip(side, work):
+                s_.wait_stream(main)
+                for x in ins:
+                    if x is not None:
+                        x.record_stream(s_)      # allocated on another stream: keep the allocator from recycling it early
+                with torch.cuda.stream(s_):
+                    outs.append(fn())
+            vid = video_branch()                 # the heavy branch stays on the caller's stream
+            for s_, o in zip(side, outs):
+                main.wait_stream(s_)
+                o.record_stream(main)
+            aud, t, av = outs
+        else:
+            aud, vid, t, av = audio_branch(), video_branch(), text_branch(), fusion_branch()
         tav = torch.cat([av, t, aud, vid], dim=1)                                                       # :495
         if check == "train":                                                                            # :497-498
             tav = engine.dropout(tav, self.dropout.p)

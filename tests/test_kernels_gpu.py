@@ -77,6 +77,20 @@ def test_gemm_epilogues(L):
     outg = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     L.gemm(A, W, outg, M=M, N=N, K=K, aux=pre, epilogue=L.EPI_GELU_BWD)
     assert rel_l2(outg, acc * x.grad) < 4e-3
+    # GELU_GRAD epilogue: the forward stores gelu'(pre) (bf16) next to gelu(pre); MUL epilogue: acc * aux (+ column sums)
+    dg = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    act2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    L.gemm(A, W, dg, M=M, N=N, K=K, bias=bias, out2=act2, epilogue=L.EPI_GELU_GRAD)
+    xe = (acc + bias).requires_grad_(True)
+    torch.nn.functional.gelu(xe).backward(torch.ones_like(xe))
+    assert rel_l2(act2, torch.nn.functional.gelu(acc + bias)) < 4e-3
+    assert rel_l2(dg, xe.grad) < 4e-3
+    assert (dg.float() - xe.grad).abs().max().item() < 8e-3          # bf16 rounding of values in [-0.13, 1.13]
+    outm = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros((N,), device="cuda")
+    L.gemm(A, W, outm, M=M, N=N, K=K, aux=dg, epilogue=L.EPI_MUL, colsum=cs)
+    assert rel_l2(outm, acc * dg.float()) < 4e-3
+    assert rel_l2(cs, (acc * dg.float()).sum(dim=0)) < 2e-3
     # fused column sums of the stored result (the bias gradient of the producing Linear), accumulated into colsum
     cs = torch.full((N,), 2.0, device="cuda")
     L.gemm(A, W, outg, M=M, N=N, K=K, aux=pre, epilogue=L.EPI_GELU_BWD, colsum=cs)
