@@ -238,19 +238,26 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             // P[j&1] must no longer be read by PV(j-2)
             if (j >= 2) mbar_wait(&p_empty[j & 1], ((j >> 1) - 1) & 1);
             tmem_st_32x32(tmem_p + lane_sel + (uint32_t)((j & 1) * 32), reinterpret_cast<uint32_t(&)[32]>(sr[0]));
-            // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+            // Every warp observes EVERY completion of pv_done (one phase per PV(j)), in order.  A parity wait can only tell
+            // "odd or even number of completions": a warp that skipped this wait and later found the barrier two phases
+            // ahead would see the parity it is waiting for as "still pending" and block forever (observed: with other
+            // kernels co-resident, or under CUPTI, PV(n-2) and PV(n-1) both retired before a warp's first epilogue poll).
+            // PV(j-1) was issued when the slowest warp finished softmax(j-1) and has retired long before softmax(j) ends.
+            if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
-                tc_fence_after();
+                // rare: the running max moved -> rescale this warp's 32 rows of O (needs PV(j-1) retired)
+                if (__any_sync(0xffffffffu, grow)) {
+                    tc_fence_after();
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t orow[32];
-                    const uint32_t to = tmem_o + lane_sel + hh * 32;
-                    tmem_ld_32x32(to, orow);
-                    tmem_ld_wait();
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t orow[32];
+                        const uint32_t to = tmem_o + lane_sel + hh * 32;
+                        tmem_ld_32x32(to, orow);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
-                    tmem_st_32x32(to, orow);
+                        for (int c = 0; c < 32; ++c) orow[c] = __float_as_uint(__uint_as_float(orow[c]) * factor);
+                        tmem_st_32x32(to, orow);
+                    }
                 }
             }
             tmem_st_wait();            // P (and a rescaled O) are in tensor memory
@@ -259,9 +266,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             if (lane == 0) mbar_arrive(&p_full[j & 1]);
         }
         // ---- epilogue: normalise and store this thread's 64-column output row (128 contiguous bytes)
-        // pv_done completes one phase per PV(j); a parity wait only tells "odd or even number of completions", and this
-        // warp is only known to be past PV(n-3) (the P-buffer hand-off): wait for PV(n-2) first, then for PV(n-1)
-        if (n_tiles >= 2) mbar_wait(pv_done, (n_tiles - 2) & 1);
+        // this warp has seen PV(0..n-2) retire inside the loop: exactly one completion, PV(n-1), is outstanding
         mbar_wait(pv_done, (n_tiles - 1) & 1);
         tc_fence_after();
         const int qrow = q0 + row;

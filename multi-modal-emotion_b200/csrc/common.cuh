@@ -288,14 +288,18 @@ TAVK_DEVINL bool mbar_test_warp(uint64_t* bar, uint32_t parity) {
         : "memory");
     return __all_sync(0xffffffffu, ok != 0);
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
-TAVK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.  The report names the
+// source line of the wait and the full block index (one line per warp).
+TAVK_DEVINL void mbar_timeout_report(int line) {
+    if ((threadIdx.x & 31) == 0)
+        printf("tavk: mbarrier wait timed out (source line %d, block %d,%d,%d warp %d)\n", line, (int)blockIdx.x,
+               (int)blockIdx.y, (int)blockIdx.z, (int)(threadIdx.x >> 5));
+    __trap();
+}
+TAVK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int line = __builtin_LINE()) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("tavk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        if (++spins > (1u << 22)) mbar_timeout_report(line);
     }
 }
 
@@ -303,14 +307,11 @@ TAVK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 // try_wait + branch loop was taking ~10x more issue slots than the warp's real work (ncu: 2.3 M executed spin
 // instructions against 0.2 M per compute instruction in the attention forward) — sleep between polls instead.
 template <int kSleepNs>
-TAVK_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+TAVK_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int line = __builtin_LINE()) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(kSleepNs);
-        if (++spins > (1u << 24)) {
-            printf("tavk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        if (++spins > (1u << 22)) mbar_timeout_report(line);
     }
 }
 
