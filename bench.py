@@ -344,9 +344,9 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
             kw["resid"] = torch.zeros((M, N), device="cuda")
         if has_rb:
             kw["rowbias"], kw["rows_per_group"] = torch.zeros((B, N), device="cuda"), max(1, M // B)
-        if epi == L.EPI_GELU:
+        if epi in (L.EPI_GELU, L.EPI_GELU_GRAD):
             kw["out2"] = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
-        if epi == L.EPI_GELU_BWD:
+        if epi in (L.EPI_GELU_BWD, L.EPI_MUL):
             kw["aux"] = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16)
         L.record_gemms = False
         # device-side duration: `reps` launches captured in a CUDA graph (eager re-launches of the small shapes are paced

@@ -49,9 +49,9 @@ def run(name, reps):
         kw["bias"] = torch.zeros(n, device="cuda")
     if hr:
         kw["resid"] = torch.zeros((m, n), device="cuda")
-    if epi == L.EPI_GELU:
+    if epi in (L.EPI_GELU, L.EPI_GELU_GRAD):
         kw["out2"] = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
-    if epi == L.EPI_GELU_BWD:
+    if epi in (L.EPI_GELU_BWD, L.EPI_MUL):
         kw["aux"] = torch.randn((m, n), device="cuda").bfloat16()
     for _ in range(2):
         L.gemm(A, B, out, **kw)
