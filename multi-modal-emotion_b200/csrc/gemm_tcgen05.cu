@@ -76,6 +76,7 @@ struct EpiItem {
     int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns (global output coordinates)
     int rows_valid;         // how many of the 32 rows lie inside the (group's) M
     bool col_ok, lead;      // column group inside the (group's) N; first K-split (applies bias / row-bias / residual)
+    int rb_group, rb_next;  // row-bias group of row_base and the first row of the next group (one division per TILE)
 };
 
 enum { OUT_F32 = 0, OUT_BF16 = 1, OUT_RED = 2 };   // plain fp32 store | bf16 store | fp32 red.global.add (split-K / +=)
@@ -87,43 +88,63 @@ struct EpiOperands {        // what one chunk needs from global memory besides t
     uint2 aux[(MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL) ? 8 : 1];
 };
 
-template <int MODE>
+// FULL: the chunk lies entirely inside the output (32 valid rows, valid column group) — the common case; every
+// predicate folds away at compile time (the predicated version spent ~100 ISETP and as many address selects per chunk).
+template <int MODE, bool FULL>
 TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, EpiOperands<MODE>& o) {
     o.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias != nullptr && w.lead && w.col_ok) o.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + w.col));
+    if (p.bias != nullptr && w.lead && (FULL || w.col_ok)) o.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + w.col));
     if (MODE == TAVK_EPI_LINEAR) {
         const bool use_res = p.resid != nullptr && w.lead;
         const bool use_rb = p.rowbias != nullptr && w.lead;
-        const float* rp = p.resid + (long long)(w.row_base + rsub) * p.ldr + w.col;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool ok = (i * 4 + rsub) < w.rows_valid && w.col_ok;
-            o.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (use_res && ok) o.res[i] = ld_global_nc_v4(rp + (long long)i * 4 * p.ldr);
-        }
-        if (use_rb) {
+        if (use_res) {
+            const float* rp = p.resid + (long long)(w.row_base + rsub) * p.ldr + w.col;
+            const long long rstep = 4 * p.ldr;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int row = w.row_base + i * 4 + rsub;
-                if ((i * 4 + rsub) < w.rows_valid && w.col_ok) {
-                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(
-                        p.rowbias + (long long)(row / p.rows_per_group) * p.N + w.col));
-                    o.res[i].x += q4.x; o.res[i].y += q4.y; o.res[i].z += q4.z; o.res[i].w += q4.w;
+                o.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FULL || ((i * 4 + rsub) < w.rows_valid && w.col_ok)) o.res[i] = ld_global_nc_v4(rp);
+                rp += rstep;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (use_rb) {
+            // the chunk's 32 rows touch the group of its first row and, past rb_next, the following one(s)
+            const float* g0 = p.rowbias + (long long)w.rb_group * p.N + w.col;
+            if (w.row_base + 32 <= w.rb_next) {            // uniform: one group for the whole chunk
+                if (FULL || w.col_ok) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(g0));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { o.res[i].x += q4.x; o.res[i].y += q4.y; o.res[i].z += q4.z; o.res[i].w += q4.w; }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = w.row_base + i * 4 + rsub;
+                    if (FULL || ((i * 4 + rsub) < w.rows_valid && w.col_ok)) {
+                        const int gi = row < w.rb_next ? w.rb_group : row / p.rows_per_group;
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)gi * p.N + w.col));
+                        o.res[i].x += q4.x; o.res[i].y += q4.y; o.res[i].z += q4.z; o.res[i].w += q4.w;
+                    }
                 }
             }
         }
     }
     if (MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL) {
         const __nv_bfloat16* ap = p.aux + (long long)(w.row_base + rsub) * p.ldaux + w.col;
+        const long long astep = 4 * p.ldaux;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             o.aux[i] = make_uint2(0u, 0u);
-            if ((i * 4 + rsub) < w.rows_valid && w.col_ok) o.aux[i] = ld_global_nc_v2(ap + (long long)i * 4 * p.ldaux);
+            if (FULL || ((i * 4 + rsub) < w.rows_valid && w.col_ok)) o.aux[i] = ld_global_nc_v2(ap);
+            ap += astep;
         }
     }
 }
 
-template <int MODE, int OUT>
+template <int MODE, int OUT, bool FULL>
 TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperands<MODE>& o, uint32_t taddr, uint32_t stg,
                              int lane, uint64_t* release_bar) {
     const int cc = lane & 7, rsub = lane >> 3;
@@ -147,20 +168,23 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
     const long long ostep = 4 * p.ldo * kEsz;
     char* op2 = nullptr;
     long long ostep2 = 0;
-    if (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD) {
+    constexpr bool kGelu = (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD);
+    if (kGelu) {
         op2 = reinterpret_cast<char*>(p.out2) + ((long long)(w.row_base + rsub) * p.ldo2 + w.col) * 2;
         ostep2 = 4 * p.ldo2 * 2;
     }
     const f32x2 alpha2 = pk(p.alpha, p.alpha), blo = pk(o.b4.x, o.b4.y), bhi = pk(o.b4.z, o.b4.w);
     f32x2 cslo = pk(0.f, 0.f), cshi = pk(0.f, 0.f);
+    const bool want_cs = !kGelu && p.colsum != nullptr;     // uniform
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rl = i * 4 + rsub;
-        const bool ok = rl < w.rows_valid && w.col_ok;
-        float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rl & 7)) << 4));
+        const bool ok = FULL || (rl < w.rows_valid && w.col_ok);
+        // row rl, 16-byte slot (cc ^ (rl & 7)): rl & 7 = rsub | ((i & 1) << 2)  (rsub < 4)
+        float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rsub | ((i & 1) << 2))) << 4));
         unpk(fma2(pk(v.x, v.y), alpha2, blo), v.x, v.y);
         unpk(fma2(pk(v.z, v.w), alpha2, bhi), v.z, v.w);
-        if (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD) {
+        if (kGelu) {
             // out = pre-activation (GELU) or gelu'(pre) (GELU_GRAD), out2 = gelu(pre); all bf16
             float4 g;
             if (MODE == TAVK_EPI_GELU) {
@@ -205,14 +229,14 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
                     *reinterpret_cast<float4*>(op) = v;
                 }
             }
-            if (p.colsum != nullptr) {      // uniform; rows past M contribute nothing
+            if (want_cs) {      // rows past M contribute nothing
                 cslo = add2(cslo, pk(ok ? v.x : 0.f, ok ? v.y : 0.f));
                 cshi = add2(cshi, pk(ok ? v.z : 0.f, ok ? v.w : 0.f));
             }
         }
         op += ostep;
     }
-    if (MODE != TAVK_EPI_GELU && MODE != TAVK_EPI_GELU_GRAD && p.colsum != nullptr) {
+    if (want_cs) {
         // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
         float cs0, cs1, cs2, cs3;
         unpk(cslo, cs0, cs1);
@@ -221,7 +245,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
         cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
         cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
         cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
-        if (lane < 8 && w.col_ok)
+        if (lane < 8 && (FULL || w.col_ok))
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + w.col), "f"(cs0), "f"(cs1),
                          "f"(cs2), "f"(cs3)
                          : "memory");
@@ -234,35 +258,56 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
                                int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
     constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     const int cc = lane & 7, rsub = lane >> 3;
-    auto item = [&](int tile, int ci) {
-        EpiItem w;
+    // per TILE (integer divisions live here, not in the per-chunk path): everything but the chunk's column
+    struct TileInfo { int row_base, rows_valid, col0, cols_left, rb_group, rb_next; bool lead; };
+    auto tile_info = [&](int tile) {
+        TileInfo t;
         const int g = tile / p.tiles_per_group;
         const int tg = tile - g * p.tiles_per_group;
         const int mn = tg / p.k_splits;
-        const int row_local = (mn / p.num_n_blocks) * kBlockM + quarter * 32;
-        const int col_local = (mn % p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32 + cc * 4;
-        w.lead = (tg % p.k_splits) == 0;
-        w.rows_valid = p.M - row_local;
-        w.row_base = g * p.out_g_row + row_local;
-        w.col = g * p.out_g_col + col_local;
-        w.col_ok = col_local < p.N;         // N % 8 == 0: a 4-column group is in or out as a whole
+        const int m_blk = mn / p.num_n_blocks;
+        const int row_local = m_blk * kBlockM + quarter * 32;
+        const int col_local = (mn - m_blk * p.num_n_blocks) * BLOCK_N + half * 32 + cc * 4;
+        t.lead = (tg - mn * p.k_splits) == 0;
+        t.rows_valid = p.M - row_local;
+        t.row_base = g * p.out_g_row + row_local;
+        t.col0 = g * p.out_g_col + col_local;
+        t.cols_left = p.N - col_local;       // N % 8 == 0: a 4-column group is in or out as a whole
+        t.rb_group = 0;
+        t.rb_next = 0x7fffffff;
+        if (MODE == TAVK_EPI_LINEAR && p.rowbias != nullptr) {
+            t.rb_group = t.row_base / p.rows_per_group;
+            t.rb_next = (t.rb_group + 1) * p.rows_per_group;
+        }
+        return t;
+    };
+    auto item = [&](const TileInfo& t, int ci) {
+        EpiItem w;
+        w.row_base = t.row_base; w.rows_valid = t.rows_valid; w.lead = t.lead;
+        w.col = t.col0 + ci * 64;
+        w.col_ok = ci * 64 < t.cols_left;
+        w.rb_group = t.rb_group; w.rb_next = t.rb_next;
         return w;
     };
     // The work of this warp is the flat sequence of (tile, chunk) items; the global operands of item i+1 are
-    // requested before item i is processed, alternating between two register buffers.
-    EpiOperands<MODE> opA, opB;
-    EpiItem wA, wB;
+    // requested before item i is processed (one chunk ahead, across tile boundaries too).
     int tile = blockIdx.x, ci = 0, it = 0;
     if (tile >= num_tiles) return;
-    wA = item(tile, 0);
-    epi_issue_loads<MODE>(p, wA, rsub, opA);
-    auto step = [&](const EpiItem& w_cur, const EpiOperands<MODE>& op_cur, EpiItem& w_nxt, EpiOperands<MODE>& op_nxt) {
+    TileInfo tcur = tile_info(tile);
+    EpiItem w_cur = item(tcur, 0), w_nxt = w_cur;
+    EpiOperands<MODE> op_cur, op_nxt;
+    if (w_cur.rows_valid >= 32 && w_cur.col_ok) epi_issue_loads<MODE, true>(p, w_cur, rsub, op_cur);
+    else epi_issue_loads<MODE, false>(p, w_cur, rsub, op_cur);
+#pragma unroll 1
+    while (true) {
         int ntile = tile, nci = ci + 1;
         if (nci == kPer) { nci = 0; ntile += (int)gridDim.x; }
         const bool more = ntile < num_tiles;
         if (more) {
-            w_nxt = item(ntile, nci);
-            epi_issue_loads<MODE>(p, w_nxt, rsub, op_nxt);
+            if (nci == 0) tcur = tile_info(ntile);
+            w_nxt = item(tcur, nci);
+            if (w_nxt.rows_valid >= 32 && w_nxt.col_ok) epi_issue_loads<MODE, true>(p, w_nxt, rsub, op_nxt);
+            else epi_issue_loads<MODE, false>(p, w_nxt, rsub, op_nxt);
         }
         const int acc = it & 1;
         if (ci == 0) {
@@ -271,15 +316,14 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + (half + 2 * ci) * 32);
         const bool last = (ci == kPer - 1);
-        epi_process<MODE, OUT>(p, w_cur, op_cur, taddr, stg, lane, last ? &tmem_empty_bar[acc] : nullptr);
+        uint64_t* rel = last ? &tmem_empty_bar[acc] : nullptr;
+        if (w_cur.rows_valid >= 32 && w_cur.col_ok) epi_process<MODE, OUT, true>(p, w_cur, op_cur, taddr, stg, lane, rel);
+        else epi_process<MODE, OUT, false>(p, w_cur, op_cur, taddr, stg, lane, rel);
         if (last) ++it;
+        if (!more) break;
         tile = ntile; ci = nci;
-        return more;
-    };
-#pragma unroll 1
-    while (true) {
-        if (!step(wA, opA, wB, opB)) break;
-        if (!step(wB, opB, wA, opA)) break;
+        w_cur = w_nxt;
+        op_cur = op_nxt;
     }
 }
 

@@ -152,65 +152,123 @@ static int launch_colsum(const void* x, int x_dtype, long long ld, const float* 
 }
 
 // ---------------------------------------------------------------- small fp32 linears
-// y[m,n] = sum_k x[m,k] w[n,k] + b[n]; one warp per output element.
-__global__ void small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                        const float* __restrict__ b, float* __restrict__ y, int M, int N, int K) {
+// fp32 end to end (the rank-1 term of the fusion attention reaches 1e7) and tiny: M = per-GPU batch rows.
+// y[m,n] = sum_k x[m,k] w[n,k] + b[n]: one warp per output column n and per tile of kSlRows rows, so a weight row is
+// read once per 8 rows (the previous warp-per-output kernel re-read W for every row: 34 us at M = 128).
+constexpr int kSlRows = 8;
+__global__ void __launch_bounds__(256)
+small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                        float* __restrict__ y, int M, int N, int K) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     const int lane = threadIdx.x & 31;
-    const long long o = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    if (o >= (long long)M * N) return;
-    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
-    const float* xr = x + (size_t)m * K;
+    const int n = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int m0 = blockIdx.y * kSlRows;
+    if (n >= N) return;
     const float* wr = w + (size_t)n * K;
-    float s = 0.f;
+    float acc[kSlRows];
+#pragma unroll
+    for (int j = 0; j < kSlRows; ++j) acc[j] = 0.f;
     if ((K & 3) == 0) {
         for (int k = lane * 4; k < K; k += 128) {
-            const float4 a = *reinterpret_cast<const float4*>(xr + k);
             const float4 c = __ldg(reinterpret_cast<const float4*>(wr + k));
-            s += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
+#pragma unroll
+            for (int j = 0; j < kSlRows; ++j) {
+                if (m0 + j < M) {
+                    const float4 a = *reinterpret_cast<const float4*>(x + (size_t)(m0 + j) * K + k);
+                    acc[j] += (a.x * c.x + a.y * c.y) + (a.z * c.z + a.w * c.w);
+                }
+            }
         }
     } else {
-        for (int k = lane; k < K; k += 32) s += xr[k] * wr[k];
-    }
-    s = warp_sum(s);
-    if (lane == 0) y[o] = s + (b ? b[n] : 0.f);
-}
-// dx[m,k] (+)= sum_n dy[m,n] w[n,k]; one thread per (m,k) and per chunk of n (blockIdx.y), 8 loads in flight,
-// partial sums combined with one atomic per thread (dx is zeroed by the host wrapper unless accumulating)
-__global__ void small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                          float* __restrict__ dx, int M, int N, int K, int n_per_chunk) {
-    pdl_wait();   // programmatic dependent launch: see common.cuh
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)M * K) return;
-    const int m = (int)(i / K), k = (int)(i - (long long)m * K);
-    const int n0 = blockIdx.y * n_per_chunk, n1 = min(n0 + n_per_chunk, N);
-    const float* dyr = dy + (size_t)m * N;
-    float s = 0.f;
-    int n = n0;
-    for (; n + 8 <= n1; n += 8) {
-        float a[8];
+        for (int k = lane; k < K; k += 32) {
+            const float c = wr[k];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = __ldg(w + (size_t)(n + j) * K + k);
+            for (int j = 0; j < kSlRows; ++j)
+                if (m0 + j < M) acc[j] += x[(size_t)(m0 + j) * K + k] * c;
+        }
+    }
+    const float bn = b ? b[n] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += dyr[n + j] * a[j];
+    for (int j = 0; j < kSlRows; ++j) {
+        const float s = warp_sum(acc[j]);
+        if (lane == 0 && m0 + j < M) y[(size_t)(m0 + j) * N + n] = s + bn;
     }
-    for (; n < n1; ++n) s += dyr[n] * __ldg(w + (size_t)n * K + k);
-    atomicAdd(dx + i, s);
 }
-// dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n,k)
-__global__ void small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                          float* __restrict__ dw, float* __restrict__ db, int M, int N, int K) {
+// dx[m,k] (+)= sum_n dy[m,n] w[n,k]: thread = one k column, block = 128 columns x one chunk of n (blockIdx.y) x one
+// tile of kSlRows rows (blockIdx.z); the dy tile sits in shared memory (broadcast reads), W[n, k..k+127] is a coalesced
+// row segment read once per row tile; partial sums are combined with one atomic per (row, column, chunk).
+constexpr int kSlChunk = 64;
+__global__ void __launch_bounds__(128)
+small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int M,
+                          int N, int K) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)N * K) return;
-    const int n = (int)(i / K), k = (int)(i - (long long)n * K);
-    float s = 0.f, sb = 0.f;
-    for (int m = 0; m < M; ++m) {
-        const float d = dy[(size_t)m * N + n];
-        s += d * x[(size_t)m * K + k];
-        sb += d;
+    __shared__ float s_dy[kSlRows][kSlChunk];
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int n0 = blockIdx.y * kSlChunk, m0 = blockIdx.z * kSlRows;
+    const int nn = min(kSlChunk, N - n0);
+    for (int i = threadIdx.x; i < kSlRows * kSlChunk; i += 128) {
+        const int j = i / kSlChunk, c = i - j * kSlChunk;
+        s_dy[j][c] = (m0 + j < M && c < nn) ? dy[(size_t)(m0 + j) * N + n0 + c] : 0.f;
     }
-    if (dw) dw[i] += s;
+    __syncthreads();
+    if (k >= K) return;
+    float acc[kSlRows];
+#pragma unroll
+    for (int j = 0; j < kSlRows; ++j) acc[j] = 0.f;
+    const float* wp = w + (size_t)n0 * K + k;
+    int c = 0;
+    for (; c + 4 <= nn; c += 4) {
+        float a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = __ldg(wp + (size_t)(c + u) * K);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < kSlRows; ++j) acc[j] += s_dy[j][c + u] * a[u];
+    }
+    for (; c < nn; ++c) {
+        const float a = __ldg(wp + (size_t)c * K);
+#pragma unroll
+        for (int j = 0; j < kSlRows; ++j) acc[j] += s_dy[j][c] * a;
+    }
+#pragma unroll
+    for (int j = 0; j < kSlRows; ++j)
+        if (m0 + j < M) atomicAdd(dx + (size_t)(m0 + j) * K + k, acc[j]);
+}
+// dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n, 4 consecutive k) when K % 4 == 0
+__global__ void __launch_bounds__(128)
+small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                          float* __restrict__ db, int M, int N, int K) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    const int kv = (K & 3) == 0 ? 4 : 1;
+    const int kq = K / kv;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * kq) return;
+    const int n = (int)(i / kq), k = (int)(i - (long long)n * kq) * kv;
+    float sb = 0.f;
+    if (kv == 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < M; ++m) {
+            const float d = __ldg(dy + (size_t)m * N + n);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * K + k));
+            s.x += d * a.x; s.y += d * a.y; s.z += d * a.z; s.w += d * a.w;
+            sb += d;
+        }
+        if (dw) {
+            float4* o = reinterpret_cast<float4*>(dw + (size_t)n * K + k);
+            float4 v = *o;
+            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+            *o = v;
+        }
+    } else {
+        float s = 0.f;
+        for (int m = 0; m < M; ++m) {
+            const float d = dy[(size_t)m * N + n];
+            s += d * x[(size_t)m * K + k];
+            sb += d;
+        }
+        if (dw) dw[(size_t)n * K + k] += s;
+    }
     if (db && k == 0) db[n] += sb;
 }
 
@@ -378,12 +436,13 @@ extern "C" int tavk_masked_colsum(const void* x, int x_dtype, int64_t ld, const 
 extern "C" int tavk_small_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K,
                                      void* stream) {
     TAVK_CHECK(x && w && y, 1, "tavk_small_linear_fwd: null pointer");
+    TAVK_CHECK((K & 3) != 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, 1,
+               "tavk_small_linear_fwd: x and w must be 16-byte aligned when K %% 4 == 0");
     if (M <= 0 || N <= 0) return 0;
-    const long long threads_total = (long long)M * N * 32;
-    const int threads = 256;
-    const long long grid = (threads_total + threads - 1) / threads;
-    TAVK_CHECK(grid < (1ll << 31), 2, "tavk_small_linear_fwd: problem too large for this kernel");
-    TAVK_CUDA(launch_kernel(small_linear_fwd_kernel, dim3((int)grid), dim3(threads), (size_t)(0), STREAM(stream), x, w, b, y, M, N, K));
+    const int gx = (N + 7) / 8;                       // 8 warps (output columns) per block
+    const int gy = (M + kSlRows - 1) / kSlRows;
+    TAVK_CHECK(gy <= 65535, 2, "tavk_small_linear_fwd: M=%d too large for this kernel", M);
+    TAVK_CUDA(launch_kernel(small_linear_fwd_kernel, dim3(gx, gy), dim3(256), (size_t)(0), STREAM(stream), x, w, b, y, M, N, K));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -394,13 +453,11 @@ extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* d
     if (M <= 0 || K <= 0) return 0;
     const long long total = (long long)M * K;
     if (!accumulate) TAVK_CUDA(cudaMemsetAsync(dx, 0, (size_t)total * sizeof(float), STREAM(stream)));
-    const int gx = (int)((total + 127) / 128);
-    int chunks = (2 * sm_count() + gx - 1) / gx;
-    if (chunks < 1) chunks = 1;
-    int npc = (N + chunks - 1) / chunks;
-    if (npc < 8) npc = 8;
-    chunks = (N + npc - 1) / npc;
-    TAVK_CUDA(launch_kernel(small_linear_bwd_x_kernel, dim3(dim3(gx, chunks)), dim3(128), (size_t)(0), STREAM(stream), dy, w, dx, M, N, K, npc));
+    if (N <= 0) return 0;
+    const int gz = (M + kSlRows - 1) / kSlRows;
+    TAVK_CHECK(gz <= 65535, 2, "tavk_small_linear_bwd_x: M=%d too large for this kernel", M);
+    TAVK_CUDA(launch_kernel(small_linear_bwd_x_kernel, dim3((K + 127) / 128, (N + kSlChunk - 1) / kSlChunk, gz), dim3(128),
+                            (size_t)(0), STREAM(stream), dy, w, dx, M, N, K));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -408,8 +465,10 @@ extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* d
 extern "C" int tavk_small_linear_bwd_w(const float* dy, const float* x, float* dw, float* db, int M, int N, int K,
                                        void* stream) {
     TAVK_CHECK(dy && x && (dw || db), 1, "tavk_small_linear_bwd_w: null pointer");
+    TAVK_CHECK((K & 3) != 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0, 1,
+               "tavk_small_linear_bwd_w: x and dw must be 16-byte aligned when K %% 4 == 0");
     if (N <= 0 || K <= 0) return 0;
-    const long long total = (long long)N * K;
+    const long long total = (long long)N * ((K & 3) == 0 ? K / 4 : K);
     TAVK_CUDA(launch_kernel(small_linear_bwd_w_kernel, dim3((int)((total + 127) / 128)), dim3(128), (size_t)(0), STREAM(stream), dy, x, dw, db, M, N, K));
     TAVK_CUDA(cudaGetLastError());
     return 0;

@@ -10,6 +10,8 @@ Constructor arguments, ``forward`` signatures, return values and ``state_dict`` 
   * the audio projection's in-features follow ``wav2vec2.config.hidden_size`` (the reference hard-codes 1024, Q13).
 Quirks that are reproduced on purpose: 12 fusion layers regardless of ``num_layers`` (Q4), plain (unmasked) mean
 pooling (Q3), the wrong-signed additive masks (Q2) that the fusion attention then adds after the softmax (Q1)."""
+import os
+
 import torch
 from torch import nn
 
@@ -24,14 +26,17 @@ _FP16_MIN = torch.finfo(torch.float16).min
 # (B*149, B*70, B*323 against VideoMAE's B*1464): alone their kernels leave most of the 148 SMs idle, together they
 # fill them.  Autograd replays each sub-graph's backward on its forward stream, so the backward overlaps the same way,
 # and a CUDA-graph capture records the fork/join as graph dependencies.
-branch_streams = True
+branch_streams = os.environ.get("TAVK_BRANCH_STREAMS", "1") != "0"
 _BRANCH_STREAMS = {}
 
 
 def _side_streams(dev):
     st = _BRANCH_STREAMS.get(dev)
     if st is None:
-        st = _BRANCH_STREAMS[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        # high priority: the side branches' kernels are short and few-CTA; letting them take free SM slots ahead of the
+        # VideoMAE branch's next wave packs them into its tails instead of queueing behind it
+        prio = -1 if os.environ.get("TAVK_BRANCH_PRIO", "1") != "0" else 0
+        st = _BRANCH_STREAMS[dev] = tuple(torch.cuda.Stream(device=dev, priority=prio) for _ in range(3))
     return st
 
 

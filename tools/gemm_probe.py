@@ -12,6 +12,8 @@ M = 23424
 SHAPES = {  # name: (M, N, K, a_mn, b_mn, epilogue, out_bf16, bias, resid, k_splits)
     "ffn_up_gelu": (M, 3072, 768, 0, 0, L.EPI_GELU, 1, 1, 0, 1),
     "ffn_up_dgrad_gelubwd": (M, 3072, 768, 0, 1, L.EPI_GELU_BWD, 1, 0, 0, 1),
+    "ffn_up_gelu_grad": (M, 3072, 768, 0, 0, L.EPI_GELU_GRAD, 1, 1, 0, 1),
+    "ffn_up_dgrad_mul": (M, 3072, 768, 0, 1, L.EPI_MUL, 1, 0, 0, 1),
     "ffn_down_resid": (M, 768, 3072, 0, 0, 0, 0, 1, 1, 1),
     "ffn_down_dgrad": (M, 768, 3072, 0, 1, 0, 0, 0, 0, 1),
     "qkv": (M, 2304, 768, 0, 0, 0, 1, 1, 0, 1),
