@@ -14,6 +14,8 @@
 // K-major operand tile  : one TMA box {64 k, rows}; UMMA desc SBO = 1024 B, K advance = +32 B per UMMA_K.
 // MN-major operand tile : rows/64 TMA boxes {64 mn, 64 k}; UMMA desc LBO = 8192 B (next 64-wide MN group),
 //                         SBO = 1024 B (next 8 k rows), K advance = +2048 B per UMMA_K.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/tavk.h"
 
@@ -61,6 +63,7 @@ struct GemmDev {
     int epilogue;
     int accumulate;
     float alpha;
+    int debug;                      // TAVK_GEMM_DEBUG (measurement only): 1 = drain TMEM and drop the tile, 2 = no global stores
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue
@@ -76,6 +79,7 @@ struct EpiItem {
     int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns (global output coordinates)
     int rows_valid;         // how many of the 32 rows lie inside the (group's) M
     bool col_ok, lead;      // column group inside the (group's) N; first K-split (applies bias / row-bias / residual)
+    bool full;              // WARP-UNIFORM: all 32 rows and all 32 columns of the chunk are inside the output
     int rb_group, rb_next;  // row-bias group of row_base and the first row of the next group (one division per TILE)
 };
 
@@ -157,6 +161,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
         __syncwarp();
         if (lane == 0) mbar_arrive(release_bar);
     }
+    if (p.debug == 1) return;       // measurement: main loop + TMEM drain only
     const uint32_t st_addr = stg + lane * 128;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -179,7 +184,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rl = i * 4 + rsub;
-        const bool ok = FULL || (rl < w.rows_valid && w.col_ok);
+        const bool ok = (FULL || (rl < w.rows_valid && w.col_ok)) && p.debug != 2;
         // row rl, 16-byte slot (cc ^ (rl & 7)): rl & 7 = rsub | ((i & 1) << 2)  (rsub < 4)
         float4 v = ld_shared_v4(stg + rl * 128 + ((cc ^ (rsub | ((i & 1) << 2))) << 4));
         unpk(fma2(pk(v.x, v.y), alpha2, blo), v.x, v.y);
@@ -267,12 +272,12 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         const int mn = tg / p.k_splits;
         const int m_blk = mn / p.num_n_blocks;
         const int row_local = m_blk * kBlockM + quarter * 32;
-        const int col_local = (mn - m_blk * p.num_n_blocks) * BLOCK_N + half * 32 + cc * 4;
+        const int col_chunk = (mn - m_blk * p.num_n_blocks) * BLOCK_N + half * 32;      // warp-uniform
         t.lead = (tg - mn * p.k_splits) == 0;
         t.rows_valid = p.M - row_local;
         t.row_base = g * p.out_g_row + row_local;
-        t.col0 = g * p.out_g_col + col_local;
-        t.cols_left = p.N - col_local;       // N % 8 == 0: a 4-column group is in or out as a whole
+        t.col0 = g * p.out_g_col + col_chunk + cc * 4;
+        t.cols_left = p.N - col_chunk;       // columns left from the first chunk's first column (warp-uniform)
         t.rb_group = 0;
         t.rb_next = 0x7fffffff;
         if (MODE == TAVK_EPI_LINEAR && p.rowbias != nullptr) {
@@ -285,7 +290,10 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         EpiItem w;
         w.row_base = t.row_base; w.rows_valid = t.rows_valid; w.lead = t.lead;
         w.col = t.col0 + ci * 64;
-        w.col_ok = ci * 64 < t.cols_left;
+        w.col_ok = ci * 64 + cc * 4 < t.cols_left;       // N % 8 == 0: a 4-column group is in or out as a whole
+        // the fast path contains warp-synchronous instructions (tcgen05.ld, __syncwarp): its condition must not depend
+        // on the lane
+        w.full = t.rows_valid >= 32 && ci * 64 + 32 <= t.cols_left;
         w.rb_group = t.rb_group; w.rb_next = t.rb_next;
         return w;
     };
@@ -296,7 +304,7 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
     TileInfo tcur = tile_info(tile);
     EpiItem w_cur = item(tcur, 0), w_nxt = w_cur;
     EpiOperands<MODE> op_cur, op_nxt;
-    if (w_cur.rows_valid >= 32 && w_cur.col_ok) epi_issue_loads<MODE, true>(p, w_cur, rsub, op_cur);
+    if (w_cur.full) epi_issue_loads<MODE, true>(p, w_cur, rsub, op_cur);
     else epi_issue_loads<MODE, false>(p, w_cur, rsub, op_cur);
 #pragma unroll 1
     while (true) {
@@ -306,7 +314,7 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         if (more) {
             if (nci == 0) tcur = tile_info(ntile);
             w_nxt = item(tcur, nci);
-            if (w_nxt.rows_valid >= 32 && w_nxt.col_ok) epi_issue_loads<MODE, true>(p, w_nxt, rsub, op_nxt);
+            if (w_nxt.full) epi_issue_loads<MODE, true>(p, w_nxt, rsub, op_nxt);
             else epi_issue_loads<MODE, false>(p, w_nxt, rsub, op_nxt);
         }
         const int acc = it & 1;
@@ -317,7 +325,7 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + (half + 2 * ci) * 32);
         const bool last = (ci == kPer - 1);
         uint64_t* rel = last ? &tmem_empty_bar[acc] : nullptr;
-        if (w_cur.rows_valid >= 32 && w_cur.col_ok) epi_process<MODE, OUT, true>(p, w_cur, op_cur, taddr, stg, lane, rel);
+        if (w_cur.full) epi_process<MODE, OUT, true>(p, w_cur, op_cur, taddr, stg, lane, rel);
         else epi_process<MODE, OUT, false>(p, w_cur, op_cur, taddr, stg, lane, rel);
         if (last) ++it;
         if (!more) break;
@@ -586,6 +594,8 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     d.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); d.ldaux = a->ldaux;
     d.colsum = a->colsum;
     d.epilogue = a->epilogue; d.accumulate = a->accumulate; d.alpha = a->alpha;
+    static const int dbg = getenv("TAVK_GEMM_DEBUG") ? atoi(getenv("TAVK_GEMM_DEBUG")) : 0;
+    d.debug = dbg;
     d.groups = groups;
     d.tiles_per_group = d.num_m_blocks * d.num_n_blocks * d.k_splits;
     d.a_kstep = a->a_kstep > 0 ? a->a_kstep : kBlockK;
