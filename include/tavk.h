@@ -50,9 +50,12 @@ int tavk_version(void);
 /* 0 when an sm_100 device is current and usable, 3 otherwise (message in tavk_last_error). */
 int tavk_device_check(void);
 int tavk_sm_count(void);
-/* The persistent GEMM uses at most tavk_sm_count() - n SMs from now on (process-wide; 0 restores the default).  Data-
- * parallel hosts reserve a few SMs for the NCCL all-reduce kernels that run concurrently with backward. */
-int tavk_reserve_sms(int n);
+/* Caller-owned scratch sizes (bytes): tavk_attn_bwd's `delta`, the GroupNorm entry points' `sums_ws`, and the GEMM (none:
+ * accumulators live in tensor memory, split-K partial sums are reduced into the output). */
+int64_t tavk_workspace_bytes_attn_bwd(int B, int S, int nh);
+int64_t tavk_workspace_bytes_groupnorm(int B, int C);
+struct tavk_gemm_args;
+int64_t tavk_workspace_bytes_gemm(const struct tavk_gemm_args* args);
 
 /* ------------------------------------------------------------------------------------------------------------
  * tavk_gemm_bf16 — C[M,N] = epi(alpha * sum_k A[m,k] * B[n,k]); bf16 operands, fp32 accumulate (tcgen05/TMEM, TMA).
@@ -103,6 +106,9 @@ typedef struct tavk_gemm_args {
     int32_t b_box_k_shift;
     int32_t out_g_row, out_g_col;
     int64_t a_rows, a_cols, b_rows, b_cols;
+    /* Per-call SM budget of the persistent grid (0 = every SM).  A data-parallel host passes tavk_sm_count() - n to keep
+     * n SMs free for the NCCL all-reduce kernels that run concurrently with backward; there is no process-wide state. */
+    int32_t max_ctas;
 } tavk_gemm_args;
 int tavk_gemm_bf16(const tavk_gemm_args* args, void* stream);
 
@@ -165,10 +171,25 @@ int tavk_embed_add_fwd(const float* x, const int64_t* idx, const float* table, f
                        void* stream);
 /* dtable[j,:] += sum_{rows: idx==j} dy[row,:]  (n_embed <= 8). */
 int tavk_embed_add_bwd(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed, void* stream);
+/* HF RobertaEmbeddings.forward up to its LayerNorm (models/tav.py:349 `bert.embeddings(input_ids)`, and inside `bert(...)`
+ * at :485): y[b,t,:] = word[ids[b,t]] + pos[p[b,t]] + type0, with p = pad_id + (count of non-pad tokens up to t) for
+ * non-pad tokens and pad_id for pad tokens; pos_ids (int64 [B,T]) receives p for the backward scatter. */
+int tavk_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, float* y,
+                           int64_t* pos_ids, int B, int T, int H, int vocab, int n_pos, int pad_id, void* stream);
+/* dtable[idx[r],:] += dy[r,:] for r < rows (idx outside [0,n_embed) skipped): embedding backward as a row scatter into a
+ * caller-owned (pre-zeroed or accumulating) table gradient. */
+int tavk_embedding_scatter_add(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed,
+                               void* stream);
 /* y[b,:] = (1/S) sum_s x[b,s,:]  — torch.mean(dim=1) at models/tav.py:478,481,488 (unmasked). */
 int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H, void* stream);
 /* dx[b,s,:] = dy[b,:] / S ; also emits a bf16 copy when dx_bf16 != NULL. */
 int tavk_mean_pool_bwd(const float* dy, float* dx, void* dx_bf16, int B, int S, int H, void* stream);
+/* Masked form (SURVEY 8b "optional mask/lengths"): y[b,:] = (1/len_b) sum_{s < len_b} x[b,s,:] with len_b = lengths[b]
+ * clamped to [0,S] (int32 [B]; NULL = the unmasked mean above; len_b = 0 gives zeros); backward: dx[b,s,:] =
+ * dy[b,:]/len_b for s < len_b, else 0. */
+int tavk_masked_mean_pool_fwd(const float* x, const int* lengths, float* y, int B, int S, int H, void* stream);
+int tavk_masked_mean_pool_bwd(const float* dy, const int* lengths, float* dx, void* dx_bf16, int B, int S, int H,
+                              void* stream);
 /* out[n] (+)= sum_m x[m,n]; x is bf16 or f32 [M,N] (row stride ld) — bias gradients. */
 int tavk_colsum(const void* x, int x_dtype, int64_t ld, float* out, int M, int N, int accumulate, void* stream);
 /* out[b,n] = sum_s w[b,s] * x[b,s,n]  (w NULL => 1) ; x bf16/f32 [B,S,N] row stride ld — the rank-1 term
@@ -193,6 +214,10 @@ int tavk_scale_f32(const float* x, float* y, float scale, int64_t n, void* strea
 int tavk_dropout(const float* x, float* y, uint8_t* keep_mask, int64_t n, float p, uint64_t seed, uint64_t offset,
                  const uint64_t* offset_dev, void* stream);
 int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float* dx, int64_t n, float p, void* stream);
+/* dx = resid + dropout_bwd(dy): the feed-forward input dropout of the reference TransformerBlock sits on a branch whose
+ * un-dropped source also feeds the residual (utils/TAVFormer.py:111,136). */
+int tavk_dropout_bwd_add(const float* dy, const uint8_t* keep_mask, const float* resid, float* dx, int64_t n, float p,
+                         void* stream);
 /* bf16 [B,S,nh,d] -> [B,nh,d,S] (inverse=0) or back (inverse=1): the reference MultiHeadAttention "concat" reinterprets
  * a [B,nh,d,S] buffer as [B,S,nh*d] (utils/TAVFormer.py:86); backward uses the inverse permutation. */
 int tavk_permute_bshd_bhds(const void* in, void* out, int B, int S, int nh, int d, int inverse, void* stream);

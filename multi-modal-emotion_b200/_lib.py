@@ -39,6 +39,7 @@ class GemmArgs(C.Structure):
         ("a_g_mn", C.c_int32), ("a_g_k", C.c_int32), ("b_g_mn", C.c_int32), ("b_g_k", C.c_int32),
         ("b_box_k_shift", C.c_int32), ("out_g_row", C.c_int32), ("out_g_col", C.c_int32),
         ("a_rows", C.c_int64), ("a_cols", C.c_int64), ("b_rows", C.c_int64), ("b_cols", C.c_int64),
+        ("max_ctas", C.c_int32),
     ]
 
 
@@ -71,7 +72,9 @@ SIGNATURES = {
     "tavk_version": [],
     "tavk_device_check": [],
     "tavk_sm_count": [],
-    "tavk_reserve_sms": [_I],
+    "tavk_workspace_bytes_attn_bwd": [_I, _I, _I],
+    "tavk_workspace_bytes_groupnorm": [_I, _I],
+    "tavk_workspace_bytes_gemm": [C.POINTER(GemmArgs)],
     "tavk_gemm_bf16": [C.POINTER(GemmArgs), _P],
     "tavk_attn_fwd": [C.POINTER(AttnArgs), _P],
     "tavk_attn_bwd": [C.POINTER(AttnBwdArgs), _P],
@@ -79,8 +82,12 @@ SIGNATURES = {
     "tavk_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_embed_add_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "tavk_embed_add_bwd": [_P, _P, _P, _I, _I, _I, _P],
+    "tavk_roberta_embed_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "tavk_embedding_scatter_add": [_P, _P, _P, _I, _I, _I, _P],
     "tavk_mean_pool_fwd": [_P, _P, _I, _I, _I, _P],
     "tavk_mean_pool_bwd": [_P, _P, _P, _I, _I, _I, _P],
+    "tavk_masked_mean_pool_fwd": [_P, _P, _P, _I, _I, _I, _P],
+    "tavk_masked_mean_pool_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "tavk_colsum": [_P, _I, _L, _P, _I, _I, _I, _P],
     "tavk_masked_colsum": [_P, _I, _L, _P, _P, _I, _I, _I, _P],
     "tavk_small_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
@@ -90,6 +97,7 @@ SIGNATURES = {
     "tavk_scale_f32": [_P, _P, _F, _L, _P],
     "tavk_dropout": [_P, _P, _P, _L, _F, _U64, _U64, _P, _P],
     "tavk_dropout_bwd": [_P, _P, _P, _L, _F, _P],
+    "tavk_dropout_bwd_add": [_P, _P, _P, _P, _L, _F, _P],
     "tavk_permute_bshd_bhds": [_P, _P, _I, _I, _I, _I, _I, _P],
     "tavk_conv0_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "tavk_groupnorm_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
@@ -102,7 +110,8 @@ SIGNATURES = {
     "tavk_adamw_prep": [_P, _P, _P, C.c_double, C.c_double, _P],
     "tavk_adamw_dev": [_P, _P, _P, _P, _P, _L, _P, C.c_double, C.c_double, _F, _F, _P, _F, _F, _I, _P],
 }
-_RESTYPES = {"tavk_last_error": C.c_char_p}
+_RESTYPES = {"tavk_last_error": C.c_char_p, "tavk_workspace_bytes_attn_bwd": C.c_int64,
+             "tavk_workspace_bytes_groupnorm": C.c_int64, "tavk_workspace_bytes_gemm": C.c_int64}
 
 _lib = None
 launch_count = 0   # library entry points invoked
@@ -153,9 +162,17 @@ def call(name, *args):
         _check(rc, name)
 
 
+gemm_reserved_sms = 0   # HOST-side policy: SMs every gemm() call leaves free (passed per call as tavk_gemm_args.max_ctas)
+
+
 def reserve_sms(n):
-    """Keep n SMs out of the persistent GEMM's grid (for concurrently running NCCL kernels)."""
-    _check(lib().tavk_reserve_sms(int(n)), "tavk_reserve_sms")
+    """Keep n SMs out of the persistent GEMM's grid (for concurrently running NCCL kernels).  The library itself holds no
+    such state: the budget travels with every call."""
+    global gemm_reserved_sms
+    n = int(n)
+    if n < 0 or n >= lib().tavk_sm_count():
+        raise TavkError("reserve_sms: %d is outside [0, %d)" % (n, lib().tavk_sm_count()))
+    gemm_reserved_sms = n
 
 
 def require_device():
@@ -189,6 +206,8 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.aux, a.ldaux = _ptr(aux), (aux.stride(0) if aux is not None else 0)
     a.colsum = _ptr(colsum)
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
+    if gemm_reserved_sms:
+        a.max_ctas = lib().tavk_sm_count() - gemm_reserved_sms
     if record_gemms:
         gemm_log.append((M, N, K, int(a_mn), int(b_mn), epilogue, int(out.dtype == torch.bfloat16), int(bias is not None),
                          int(resid is not None), int(rowbias is not None), int(accumulate), k_splits,

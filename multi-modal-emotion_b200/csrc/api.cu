@@ -31,15 +31,6 @@ int sm_count() {
     return cached[dev];
 }
 
-// SMs the persistent GEMM leaves to other work.  Data-parallel runs reserve a few for the NCCL all-reduce kernels: a
-// persistent one-CTA-per-SM GEMM otherwise owns every SM, NCCL's CTAs only get in at kernel boundaries, and the
-// GEMM CTAs they displace start late — with a static tile schedule the whole kernel then waits for them.
-static int g_reserved_sms = 0;
-int gemm_sm_budget() {
-    const int n = sm_count() - g_reserved_sms;
-    return n < 1 ? 1 : n;
-}
-
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -60,13 +51,18 @@ extern "C" int tavk_version(void) { return TAVK_VERSION; }
 
 extern "C" int tavk_sm_count(void) { return tavk::sm_count(); }
 
-extern "C" int tavk_reserve_sms(int n) {
-    if (n < 0 || n >= tavk::sm_count()) {
-        tavk::set_error("tavk_reserve_sms: %d is outside [0, %d)", n, tavk::sm_count());
-        return 1;
-    }
-    tavk::g_reserved_sms = n;
-    return 0;
+// Workspace sizes of the entry points that need caller-owned scratch (everything else needs none).
+extern "C" int64_t tavk_workspace_bytes_attn_bwd(int B, int S, int nh) {
+    if (B <= 0 || S <= 0 || nh <= 0) return 0;
+    return (int64_t)B * nh * S * (int64_t)sizeof(float);            // tavk_attn_bwd_args.delta: f32 [B, nh, S]
+}
+extern "C" int64_t tavk_workspace_bytes_groupnorm(int B, int C) {
+    if (B <= 0 || C <= 0) return 0;
+    return (int64_t)B * 2 * C * (int64_t)sizeof(float);             // sums_ws: f32 [B, 2, C]
+}
+extern "C" int64_t tavk_workspace_bytes_gemm(const tavk_gemm_args* a) {
+    (void)a;
+    return 0;   // accumulators live in tensor memory, split-K partial sums go straight to the output (red.global.add)
 }
 
 extern "C" int tavk_device_check(void) {

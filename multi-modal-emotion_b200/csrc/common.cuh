@@ -31,7 +31,6 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 int sm_count();
-int gemm_sm_budget();   // sm_count() minus the SMs reserved through tavk_reserve_sms()
 bool pdl_enabled();   // programmatic dependent launch: opt-in with TAVK_PDL=1 (see api.cu for the measurement)
 
 // Launch with the programmatic-stream-serialization attribute: the grid may be scheduled while its predecessor on the

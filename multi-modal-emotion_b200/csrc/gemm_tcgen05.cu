@@ -63,7 +63,8 @@ struct GemmDev {
     int epilogue;
     int accumulate;
     float alpha;
-    int debug;                      // TAVK_GEMM_DEBUG (measurement only): 1 = drain TMEM and drop the tile, 2 = no global stores
+    int debug;                      // TAVK_GEMM_DEBUG (measurement only): 1 = drain TMEM and drop the tile, 2 = no global stores,
+                                    // 3 = stores folded onto 128 rows (no DRAM write-back)
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue
@@ -169,13 +170,15 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
     __syncwarp();
     // this lane's first output element; rows advance by 4 per step (pointer increments instead of 64-bit multiplies)
     constexpr int kEsz = (OUT == OUT_BF16) ? 2 : 4;
-    char* op = reinterpret_cast<char*>(p.out) + ((long long)(w.row_base + rsub) * p.ldo + w.col) * kEsz;
+    // debug 3 (measurement only): same stores, but every tile lands on the first 128 rows (L2-resident: no DRAM write-back)
+    const int orow = (p.debug == 3 ? (w.row_base & 127) : w.row_base) + rsub;
+    char* op = reinterpret_cast<char*>(p.out) + ((long long)orow * p.ldo + w.col) * kEsz;
     const long long ostep = 4 * p.ldo * kEsz;
     char* op2 = nullptr;
     long long ostep2 = 0;
     constexpr bool kGelu = (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD);
     if (kGelu) {
-        op2 = reinterpret_cast<char*>(p.out2) + ((long long)(w.row_base + rsub) * p.ldo2 + w.col) * 2;
+        op2 = reinterpret_cast<char*>(p.out2) + ((long long)orow * p.ldo2 + w.col) * 2;
         ostep2 = 4 * p.ldo2 * 2;
     }
     const f32x2 alpha2 = pk(p.alpha, p.alpha), blo = pk(o.b4.x, o.b4.y), bhi = pk(o.b4.z, o.b4.w);
@@ -567,7 +570,8 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
                "tavk_gemm_bf16: a_kstep needs a K-major A operand and a multiple of 8 elements");
 
     // tile-shape heuristic: the widest tile whose wave quantisation is not noticeably worse than a narrower one's
-    const int sms = gemm_sm_budget();
+    // per-call SM budget (a data-parallel host keeps a few SMs free for concurrently running NCCL kernels)
+    const int sms = (a->max_ctas > 0 && a->max_ctas < sm_count()) ? a->max_ctas : sm_count();
     const int mblocks = (a->M + kBlockM - 1) / kBlockM;
     auto waves_eff = [&](int bn) {
         const long long tiles = (long long)groups * mblocks * ((a->N + bn - 1) / bn) * k_splits;

@@ -46,15 +46,72 @@ __global__ void embed_add_bwd_kernel(const float* __restrict__ dy, const int64_t
         if (k < n_embed && acc[k] != 0.f) atomicAdd(dtable + (size_t)k * H + c, acc[k]);
 }
 
+// ---------------------------------------------------------------- RoBERTa input embeddings (models/tav.py:349,485)
+// HF RobertaEmbeddings.forward up to (not including) its LayerNorm: y[b,t,:] = word[ids[b,t]] + pos[p[b,t]] + type[0],
+// p = padding_idx + (running count of non-pad tokens) for non-pad tokens, padding_idx for pad tokens
+// (create_position_ids_from_input_ids).  One block per sequence: thread 0 scans the T ids into shared memory.
+__global__ void __launch_bounds__(256)
+roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float4* __restrict__ word, const float4* __restrict__ pos,
+                         const float4* __restrict__ type0, float4* __restrict__ y, int64_t* __restrict__ pos_ids, int T,
+                         int H4, int V, int P, int pad) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    extern __shared__ int s_pos[];
+    const int b = blockIdx.x;
+    const int64_t* row = ids + (size_t)b * T;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < T; ++t) {
+            const bool tok = row[t] != pad;
+            run += tok ? 1 : 0;
+            int pi = tok ? run + pad : pad;
+            pi = pi < 0 ? 0 : (pi >= P ? P - 1 : pi);
+            s_pos[t] = pi;
+            pos_ids[(size_t)b * T + t] = pi;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * H4; i += blockDim.x) {
+        const int t = i / H4, c = i - t * H4;
+        long long w = row[t];
+        w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+        const float4 a = __ldg(word + (size_t)w * H4 + c), p4 = __ldg(pos + (size_t)s_pos[t] * H4 + c), t4 = __ldg(type0 + c);
+        y[((size_t)b * T + t) * H4 + c] = make_float4((a.x + t4.x) + p4.x, (a.y + t4.y) + p4.y, (a.z + t4.z) + p4.z, (a.w + t4.w) + p4.w);   // HF order
+    }
+}
+// dtable[idx[r], :] += dy[r, :]  (row scatter with vector reductions; the table gradient is never materialised densely
+// by this call: it accumulates into whatever buffer the caller owns, e.g. the parameter's slice of the flat gradient)
+__global__ void embedding_scatter_add_kernel(const float* __restrict__ dy, const int64_t* __restrict__ idx,
+                                             float* __restrict__ dtable, int rows, int H4, int n_embed) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    const long long total = (long long)rows * H4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / H4), c = (int)(i - (long long)r * H4);
+        const long long j = idx[r];
+        if (j < 0 || j >= n_embed) continue;
+        const float4 v = reinterpret_cast<const float4*>(dy)[i];
+        float* o = dtable + ((size_t)j * H4 + c) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- mean pool (models/tav.py:478,481,488)
+// `lengths` (int32 [B] or NULL): masked mean over the first lengths[b] rows of sample b (divisor lengths[b]); NULL = all S
+// rows (the reference pools unmasked; the masked form is the boundary's optional argument).
 __global__ void mean_pool_fwd_kernel(const float4* __restrict__ x, float* __restrict__ y, int S, int H4,
-                                     int rows_per_chunk, float inv_s) {
+                                     int rows_per_chunk, float inv_s, const int* __restrict__ lengths) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= H4) return;
     const int b = blockIdx.z;
+    int len = S;
+    if (lengths != nullptr) {
+        len = min(max(lengths[b], 0), S);
+        inv_s = len > 0 ? 1.0f / (float)len : 0.f;
+    }
     const int s0 = blockIdx.y * rows_per_chunk;
-    const int s1 = min(s0 + rows_per_chunk, S);
+    const int s1 = min(s0 + rows_per_chunk, len);
+    if (s0 >= s1) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* xb = x + (size_t)b * S * H4;
     for (int s = s0; s < s1; ++s) {
@@ -69,15 +126,21 @@ __global__ void mean_pool_fwd_kernel(const float4* __restrict__ x, float* __rest
 }
 
 __global__ void mean_pool_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx,
-                                     uint2* __restrict__ dx_bf16, int S, int H4, long long total, float inv_s) {
+                                     uint2* __restrict__ dx_bf16, int S, int H4, long long total, float inv_s,
+                                     const int* __restrict__ lengths) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / H4;
         const int c = (int)(i - row * H4);
         const int b = (int)(row / S);
+        float sc = inv_s;
+        if (lengths != nullptr) {
+            const int len = min(max(lengths[b], 0), S);
+            sc = ((int)(row - (long long)b * S) < len) ? 1.0f / (float)len : 0.f;
+        }
         float4 v = __ldg(dy + (size_t)b * H4 + c);
-        v.x *= inv_s; v.y *= inv_s; v.z *= inv_s; v.w *= inv_s;
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
         if (dx) dx[i] = v;
         if (dx_bf16) dx_bf16[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
@@ -317,6 +380,15 @@ __global__ void dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
         dx[i] = keep[i] ? dy[i] * inv_keep : 0.f;
 }
 
+__global__ void dropout_bwd_add_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ keep,
+                                       const float* __restrict__ resid, float* __restrict__ dx, long long n,
+                                       float inv_keep) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+        dx[i] = resid[i] + (keep[i] ? dy[i] * inv_keep : 0.f);
+}
+
 // [B,S,nh,d] -> [B,nh,d,S] (the reference MultiHeadAttention "concat" quirk, utils/TAVFormer.py:86)
 // via a 32x32 smem transpose of the (S, d) plane of every (b, h); `inverse` maps back (used in backward).
 __global__ void permute_bshd_bhds_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int S,
@@ -392,7 +464,41 @@ extern "C" int tavk_embed_add_bwd(const float* dy, const int64_t* idx, float* dt
     return 0;
 }
 
+extern "C" int tavk_masked_mean_pool_fwd(const float* x, const int* lengths, float* y, int B, int S, int H, void* stream);
+extern "C" int tavk_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0,
+                                      float* y, int64_t* pos_ids, int B, int T, int H, int vocab, int n_pos, int pad_id,
+                                      void* stream) {
+    TAVK_CHECK(ids && word && pos && type0 && y && pos_ids, 1, "tavk_roberta_embed_fwd: null pointer");
+    TAVK_CHECK(H % 4 == 0 && T >= 1 && T <= 8192, 1, "tavk_roberta_embed_fwd: bad shape T=%d H=%d", T, H);
+    TAVK_CHECK(((reinterpret_cast<uintptr_t>(word) | reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(type0) |
+                 reinterpret_cast<uintptr_t>(y)) & 15) == 0, 1, "tavk_roberta_embed_fwd: tables and output must be 16-byte aligned");
+    if (B <= 0) return 0;
+    TAVK_CUDA(launch_kernel(roberta_embed_fwd_kernel, dim3(B), dim3(256), (size_t)T * sizeof(int), STREAM(stream), ids,
+                            reinterpret_cast<const float4*>(word), reinterpret_cast<const float4*>(pos),
+                            reinterpret_cast<const float4*>(type0), reinterpret_cast<float4*>(y), pos_ids, T, H / 4, vocab,
+                            n_pos, pad_id));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_embedding_scatter_add(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed,
+                                          void* stream) {
+    TAVK_CHECK(dy && idx && dtable, 1, "tavk_embedding_scatter_add: null pointer");
+    TAVK_CHECK(H % 4 == 0, 1, "tavk_embedding_scatter_add: H=%d must be a multiple of 4", H);
+    TAVK_CHECK(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dtable)) & 15) == 0, 1,
+               "tavk_embedding_scatter_add: buffers must be 16-byte aligned");
+    if (rows <= 0) return 0;
+    const long long total = (long long)rows * (H / 4);
+    TAVK_CUDA(launch_kernel(embedding_scatter_add_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), STREAM(stream), dy, idx, dtable,
+                            rows, H / 4, n_embed));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H, void* stream) {
+    return tavk_masked_mean_pool_fwd(x, nullptr, y, B, S, H, stream);
+}
+extern "C" int tavk_masked_mean_pool_fwd(const float* x, const int* lengths, float* y, int B, int S, int H, void* stream) {
     TAVK_CHECK(x && y, 1, "tavk_mean_pool_fwd: null pointer");
     TAVK_CHECK(H % 4 == 0, 1, "tavk_mean_pool_fwd: H=%d must be a multiple of 4", H);
     if (B <= 0) return 0;
@@ -406,19 +512,25 @@ extern "C" int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H,
     if (rpc < 8) rpc = 8;
     chunks = (S + rpc - 1) / rpc;
     TAVK_CUDA(launch_kernel(mean_pool_fwd_kernel, dim3(dim3(gx, chunks, B)), dim3(threads), (size_t)(0), STREAM(stream), reinterpret_cast<const float4*>(x), y, S,
-                                                                            H / 4, rpc, 1.0f / (float)S));
+                                                                            H / 4, rpc, 1.0f / (float)S, lengths));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
 
+extern "C" int tavk_masked_mean_pool_bwd(const float* dy, const int* lengths, float* dx, void* dx_bf16, int B, int S, int H,
+                                         void* stream);
 extern "C" int tavk_mean_pool_bwd(const float* dy, float* dx, void* dx_bf16, int B, int S, int H, void* stream) {
+    return tavk_masked_mean_pool_bwd(dy, nullptr, dx, dx_bf16, B, S, H, stream);
+}
+extern "C" int tavk_masked_mean_pool_bwd(const float* dy, const int* lengths, float* dx, void* dx_bf16, int B, int S, int H,
+                                         void* stream) {
     TAVK_CHECK(dy && (dx || dx_bf16), 1, "tavk_mean_pool_bwd: null pointer");
     TAVK_CHECK(H % 4 == 0, 1, "tavk_mean_pool_bwd: H=%d must be a multiple of 4", H);
     if (B <= 0 || S <= 0) return 0;
     const long long total = (long long)B * S * (H / 4);
     TAVK_CUDA(launch_kernel(mean_pool_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), STREAM(stream), 
         reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), reinterpret_cast<uint2*>(dx_bf16), S, H / 4,
-        total, 1.0f / (float)S));
+        total, 1.0f / (float)S, lengths));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -509,6 +621,17 @@ extern "C" int tavk_dropout_bwd(const float* dy, const uint8_t* keep_mask, float
     TAVK_CHECK(dy && dx && keep_mask, 1, "tavk_dropout_bwd: null pointer");
     if (n <= 0) return 0;
     TAVK_CUDA(launch_kernel(dropout_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), STREAM(stream), dy, keep_mask, dx, n, 1.0f / (1.0f - p)));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_dropout_bwd_add(const float* dy, const uint8_t* keep_mask, const float* resid, float* dx, int64_t n,
+                                    float p, void* stream) {
+    TAVK_CHECK(dy && dx && keep_mask && resid, 1, "tavk_dropout_bwd_add: null pointer");
+    TAVK_CHECK(p >= 0.f && p < 1.f, 1, "tavk_dropout_bwd_add: p=%f out of [0,1)", (double)p);
+    if (n <= 0) return 0;
+    TAVK_CUDA(launch_kernel(dropout_bwd_add_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), STREAM(stream), dy, keep_mask, resid, dx, n,
+                            1.0f / (1.0f - p)));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

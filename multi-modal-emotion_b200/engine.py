@@ -36,6 +36,8 @@ class LayerSpec:
     eps: float = 1e-12
     mask_mode: str = "none"      # "none" | "key_bias" (pre-softmax additive) | "rank1" (post-softmax additive, Q1)
     scrambled_concat: bool = False  # reference MultiHeadAttention concat quirk (Q5)
+    dropout: float = 0.0         # post-LN blocks only: the reference TransformerBlock's three nn.Dropout(p) in training mode
+    dropout_salt: int = 0        # distinguishes the random streams of different encoders
 
 
 # flat parameter order per layer (None allowed for absent biases)
@@ -176,7 +178,7 @@ def _bf16(shape, dev):
 
 class _Saved:
     __slots__ = ("x", "x_bf", "h1", "mean1", "rstd1", "qkv", "o", "o_used", "lse", "c", "x1", "h2", "mean2", "rstd2",
-                 "pre", "act", "f")
+                 "pre", "act", "f", "drop")
 
     def __init__(self):
         for s in self.__slots__:
@@ -193,7 +195,35 @@ def _attention_fwd(spec, qkv, B, S, key_bias):
     return o, lse
 
 
-def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
+debug_dropout_masks = None   # tests set this to a list: every keep-mask drawn by the layer engine is appended (uint8)
+
+
+def _drop_fwd(x, p, li, site, spec):
+    """nn.Dropout(p) in training mode on an fp32 [M,H] buffer: (y, keep_mask uint8).  Counter-based generator keyed on
+    (torch.initial_seed(), encoder salt, layer, site) plus the device-side step counter (fresh masks on graph replays)."""
+    c = _dropout_counter.get(x.device)
+    if c is None:
+        c = _dropout_counter[x.device] = torch.zeros(1, dtype=torch.int64, device=x.device)
+    y = torch.empty_like(x)
+    keep = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    stream_id = ((spec.dropout_salt & 0xFFFF) << 16) | ((li * 4 + site) & 0xFFFF)
+    seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (stream_id + 1)) & 0x7FFFFFFFFFFFFFFF
+    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), float(p), seed, 0, c.data_ptr())
+    if debug_dropout_masks is not None:
+        debug_dropout_masks.append(keep)
+    return y, keep
+
+
+def _drop_bwd(dy, keep, p, resid=None):
+    dx = torch.empty_like(dy)
+    if resid is None:
+        L.call("tavk_dropout_bwd", dy.data_ptr(), keep.data_ptr(), dx.data_ptr(), dy.numel(), float(p))
+    else:
+        L.call("tavk_dropout_bwd_add", dy.data_ptr(), keep.data_ptr(), resid.data_ptr(), dx.data_ptr(), dy.numel(), float(p))
+    return dx
+
+
+def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0):
     """x: f32 [M,H].  Returns (y_f32, y_bf16 or None, saved)."""
     H, I = spec.hidden, spec.inter
     M = B * S
@@ -237,15 +267,29 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep):
         L.call("tavk_permute_bshd_bhds", o.data_ptr(), o_used.data_ptr(), B, S, spec.heads, H // spec.heads, 0)
     a = _f32((M, H), dev)
     L.gemm(o_used, sh.wo, a, M=M, N=H, K=H, bias=d["bo"], resid=x)
+    pd = spec.dropout
+    drop = None
+    if pd > 0.0:
+        # reference TransformerBlock in training mode (utils/TAVFormer.py:130-141): dropout1 on the residual sum before
+        # norm1, the Dropout that opens feed_forward (the FFN residual keeps the un-dropped norm1 output), dropout2
+        # before norm2
+        a, m1 = _drop_fwd(a, pd, li, 0, spec)
     y_bf, y_f32, mean1, rstd1 = L.layernorm_fwd(a, d["ln1_w"], d["ln1_b"], spec.eps, want_bf16=True, want_f32=True)
+    ff_in = y_bf
+    if pd > 0.0:
+        yd, m2 = _drop_fwd(y_f32, pd, li, 1, spec)
+        ff_in = L.cast_bf16(yd)
     pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
-    L.gemm(y_bf, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
+    L.gemm(ff_in, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
     f = _f32((M, H), dev)
     L.gemm(act, sh.w2, f, M=M, N=H, K=I, bias=d["b2"], resid=y_f32)
+    if pd > 0.0:
+        f, m3 = _drop_fwd(f, pd, li, 2, spec)
+        drop = (m1, m2, m3)
     z_bf, z_f32, mean2, rstd2 = L.layernorm_fwd(f, d["ln2_w"], d["ln2_b"], spec.eps, want_bf16=True, want_f32=True)
     if keep:
         sv.x_bf, sv.qkv, sv.o, sv.o_used, sv.lse, sv.x1, sv.mean1, sv.rstd1 = x_bf, qkv, o, o_used, lse, a, mean1, rstd1
-        sv.h2, sv.pre, sv.act, sv.f, sv.mean2, sv.rstd2 = y_bf, pre, act, f, mean2, rstd2
+        sv.h2, sv.pre, sv.act, sv.f, sv.mean2, sv.rstd2, sv.drop = ff_in, pre, act, f, mean2, rstd2, drop
     return z_f32, z_bf, sv
 
 
@@ -350,16 +394,37 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
         dx, dx_bf = L.layernorm_bwd(dh1, sv.x, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
                                     resid=dx1, want_f32=True, want_bf16=need_dx_bf, dx_colsum=dx_colsum)
     else:
-        df, df_bf = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
-                                    want_f32=True, want_bf16=True, dx_colsum=go.target("b2"))
+        pd = spec.dropout if sv.drop is not None else 0.0
+        if pd > 0.0:
+            # gradients of the three dropouts (see _layer_fwd): the LayerNorm backward can no longer emit the bias column
+            # sums or the bf16 copies itself, because both are taken AFTER the dropout mask is applied
+            df, _ = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
+                                    want_f32=True, want_bf16=False)
+            df = _drop_bwd(df, sv.drop[2], pd)
+            df_bf = L.cast_bf16(df)
+            if d["b2"] is not None:
+                L.colsum(df, go.target("b2"), M=M, N=H, accumulate=True)
+        else:
+            df, df_bf = L.layernorm_bwd(dy, sv.f, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
+                                        want_f32=True, want_bf16=True, dx_colsum=go.target("b2"))
         _wgrad(df_bf, sv.act, H, I, M, out=go.target("w2"))
         dpre = _bf16((M, I), dev)
         L.gemm(df_bf, sh.w2, dpre, M=M, N=I, K=H, b_mn=True, aux=sv.pre, epilogue=L.EPI_MUL, colsum=go.target("b1"))
         _wgrad(dpre, sv.h2, I, H, M, out=go.target("w1"))
         dyl = _f32((M, H), dev)
-        L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)
-        da, da_bf = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
-                                    want_f32=True, want_bf16=True, dx_colsum=go.target("bo"))
+        if pd > 0.0:
+            L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True)
+            dyl = _drop_bwd(dyl, sv.drop[1], pd, resid=df)
+            da, _ = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
+                                    want_f32=True, want_bf16=False)
+            da = _drop_bwd(da, sv.drop[0], pd)
+            da_bf = L.cast_bf16(da)
+            if d["bo"] is not None:
+                L.colsum(da, go.target("bo"), M=M, N=H, accumulate=True)
+        else:
+            L.gemm(dpre, sh.w1, dyl, M=M, N=H, K=I, b_mn=True, resid=df)
+            da, da_bf = L.layernorm_bwd(dyl, sv.x1, sv.mean1, sv.rstd1, d["ln1_w"], go.target("ln1_w"), go.target("ln1_b"),
+                                        want_f32=True, want_bf16=True, dx_colsum=go.target("bo"))
         _wgrad(da_bf, sv.o_used, H, H, M, out=go.target("wo"))
         do = _bf16((M, H), dev)
         L.gemm(da_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
@@ -393,8 +458,10 @@ class EncoderStackFn(torch.autograd.Function):
         for li in range(n_layers):
             p = params[li * N_SLOTS:(li + 1) * N_SLOTS]
             sh = shadows[li].refresh(p, spec)
-            cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep)
+            cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep, li)
             saved.append(sv)
+        if spec.dropout > 0.0 and not spec.pre_ln:
+            _dropout_counter[x.device].add_(1)   # device-side: the next call (or graph replay) draws fresh masks
         ctx.spec, ctx.shadows, ctx.saved, ctx.mask2d, ctx.params, ctx.dims = spec, shadows, saved, mask2d, params, (B, S, H)
         return cur.view(B, S, H)
 
@@ -467,12 +534,15 @@ def layer_norm(x, w, b, eps=1e-5):
 
 class _MeanPoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, lengths):
         B, S, H = x.shape
         x = x.contiguous().float()
         y = torch.empty((B, H), dtype=torch.float32, device=x.device)
-        L.call("tavk_mean_pool_fwd", x.data_ptr(), y.data_ptr(), B, S, H)
+        if lengths is not None:
+            lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        L.call("tavk_masked_mean_pool_fwd", x.data_ptr(), L._ptr(lengths), y.data_ptr(), B, S, H)
         ctx.dims = (B, S, H)
+        ctx.lengths = lengths
         return y
 
     @staticmethod
@@ -480,13 +550,15 @@ class _MeanPoolFn(torch.autograd.Function):
         B, S, H = ctx.dims
         dy = dy.contiguous().float()
         dx = torch.empty((B, S, H), dtype=torch.float32, device=dy.device)
-        L.call("tavk_mean_pool_bwd", dy.data_ptr(), dx.data_ptr(), None, B, S, H)
-        return dx
+        L.call("tavk_masked_mean_pool_bwd", dy.data_ptr(), L._ptr(ctx.lengths), dx.data_ptr(), None, B, S, H)
+        return dx, None
 
 
-def mean_pool(x):
-    """torch.mean(x, dim=1) (reference models/tav.py:478,481,488; unmasked — SURVEY Q3)."""
-    return _MeanPoolFn.apply(x)
+def mean_pool(x, lengths=None):
+    """torch.mean(x, dim=1) (reference models/tav.py:478,481,488; unmasked — SURVEY Q3).  ``lengths`` (int [B]) selects the
+    masked mean over the first lengths[b] tokens of each sample instead (the boundary's optional argument; the
+    reference itself never passes one)."""
+    return _MeanPoolFn.apply(x, lengths)
 
 
 class _EmbedAddFn(torch.autograd.Function):
@@ -516,6 +588,70 @@ class _EmbedAddFn(torch.autograd.Function):
 def embed_add(x, idx, table):
     """x + table[idx] (reference models/tav.py:474)."""
     return _EmbedAddFn.apply(x, idx, table)
+
+
+class _RobertaEmbedFn(torch.autograd.Function):
+    """word[ids] + type[0] + pos[position ids] (HF RobertaEmbeddings before its LayerNorm) as one gather kernel; the
+    backward scatters rows straight into the tables' gradients — into the parameter's own ``.grad`` slice of the flat
+    buffer when the fused optimiser owns it (gradient sink), so the 154 MB word-embedding gradient is never zero-filled,
+    written and added as three dense passes."""
+
+    @staticmethod
+    def forward(ctx, ids, word, pos, typ, pad_id):
+        B, T = ids.shape
+        V, H = word.shape
+        ids = ids.contiguous().long()
+        y = torch.empty((B, T, H), dtype=torch.float32, device=word.device)
+        pos_ids = torch.empty((B, T), dtype=torch.int64, device=word.device)
+        L.call("tavk_roberta_embed_fwd", ids.data_ptr(), word.data_ptr(), pos.data_ptr(), typ.data_ptr(), y.data_ptr(),
+               pos_ids.data_ptr(), B, T, H, V, pos.shape[0], int(pad_id))
+        ctx.save_for_backward(ids, pos_ids)
+        ctx.tables = (word, pos, typ)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, pos_ids = ctx.saved_tensors
+        word, pos, typ = ctx.tables
+        B, T = ids.shape
+        H = word.shape[1]
+        dy = dy.contiguous().float()
+        outs, written = [], []
+        for table, idx, need in ((word, ids, ctx.needs_input_grad[1]), (pos, pos_ids, ctx.needs_input_grad[2])):
+            if not need:
+                outs.append(None)
+                continue
+            g = _sink(table)
+            if g is None:
+                g = torch.zeros_like(table)
+                outs.append(g)
+            else:
+                outs.append(None)
+                written.append(table)
+            L.call("tavk_embedding_scatter_add", dy.data_ptr(), idx.data_ptr(), g.data_ptr(), B * T, H, table.shape[0])
+        dtyp = None
+        if ctx.needs_input_grad[3]:
+            g = _sink(typ)
+            if g is None:
+                dtyp = torch.zeros_like(typ)
+                g = dtyp
+            else:
+                written.append(typ)
+            colsum_target = g[0]          # every token uses type row 0
+            L.colsum(dy.view(B * T, H), colsum_target, M=B * T, N=H, accumulate=True)
+        if grad_written_hook is not None and written:
+            grad_written_hook(written)
+        return None, outs[0], outs[1], dtyp, None
+
+
+def roberta_embeddings(emb, input_ids):
+    """HF RobertaEmbeddings.forward(input_ids=...) (reference models/tav.py:349 and inside bert(...) at :485): gather-sum
+    kernel, then the LayerNorm kernel (dropout: the HF sub-models stay in eval mode)."""
+    if emb.training and emb.dropout.p > 0:
+        raise NotImplementedError("RobertaEmbeddings dropout in training mode (the reference keeps the HF models in eval)")
+    x = _RobertaEmbedFn.apply(input_ids, emb.word_embeddings.weight, emb.position_embeddings.weight,
+                              emb.token_type_embeddings.weight, emb.padding_idx)
+    return layer_norm(x, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
 
 
 class _SmallLinearFn(torch.autograd.Function):

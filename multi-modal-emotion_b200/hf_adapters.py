@@ -71,7 +71,7 @@ def run_roberta(model, input_ids, attention_mask):
     pooler tanh(W h[:,0] + b)."""
     c = model.config
     _check_head_dim(c.hidden_size, c.num_attention_heads)
-    x = model.embeddings(input_ids=input_ids)
+    x = engine.roberta_embeddings(model.embeddings, input_ids)
     B, S, _ = x.shape
     bias = None
     if attention_mask is not None:
@@ -96,11 +96,20 @@ def wav2vec2_layer_slots(lyr):
             ff.output_dense.bias]
 
 
+def feature_projection(model, feats):
+    """HF Wav2Vec2FeatureProjection.forward (LayerNorm over the conv channels + Linear C -> H; dropout p = 0 in eval) on
+    the LayerNorm kernel and the tcgen05 GEMM (reference models/tav.py:356 and inside wav2vec2(...) at :476)."""
+    fp = model.feature_projection
+    if fp.training and fp.dropout.p > 0:
+        raise NotImplementedError("feature_projection dropout in training mode (the reference keeps the HF models in eval)")
+    h = engine.layer_norm(feats, fp.layer_norm.weight, fp.layer_norm.bias, fp.layer_norm.eps)
+    return engine.linear_bf16(h, fp.projection.weight, fp.projection.bias)
+
+
 def wav2vec2_front(model, wav):
     """feature_extractor (7 x Conv1d) -> transpose -> feature_projection (LN + Linear): [B,L] -> [B,Ta,H]."""
     feats = frontends.feature_extractor_cl(model, wav)      # channels-last [B, frames, C]
-    hidden, _ = model.feature_projection(feats)
-    return hidden
+    return feature_projection(model, feats)
 
 
 def wav2vec2_encoder(model, hidden):

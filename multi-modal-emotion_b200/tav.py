@@ -123,6 +123,11 @@ class PreFormer(nn.Module):
         B, T, H = hidden_states.shape
         if not getattr(c, "apply_spec_augment", True) or T < c.mask_time_length or not training:
             return hidden_states
+        if hidden_states.is_cuda and torch.cuda.is_current_stream_capturing():
+            # the mask indices come from numpy's host generator (HF _compute_mask_indices, as in the reference): a
+            # captured graph would replay ONE mask forever
+            raise RuntimeError("SpecAugment (apply_spec_augment=True) draws its masks on the host and cannot be captured "
+                               "in a CUDA graph: run the step eagerly (use_cuda_graph=False) or disable it in the config")
         from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
 
         hidden_states = hidden_states.clone()
@@ -156,12 +161,12 @@ class PreFormer(nn.Module):
         text_mask, audio_mask, visual_mask = to(text_mask), to(audio_mask), to(visual_mask)
         # text (models/tav.py:349)
         if input_ids is not None:
-            embedded_bert = self.bert.embeddings(input_ids=input_ids)
+            embedded_bert = engine.roberta_embeddings(self.bert.embeddings, input_ids)
         # audio (:352-363)
         feats = frontends.feature_extractor_cl(self.wav2vec2, audio_features)    # channels-last [B, frames, C]
         if audio_mask is not None:
             audio_mask = self._get_feature_vector_attention_mask(feats.shape[1], audio_mask, add_adapter=False)
-        embedded_audio, _ = self.wav2vec2.feature_projection(feats)
+        embedded_audio = hf.feature_projection(self.wav2vec2, feats)
         embedded_audio = self._mask_hidden_states(embedded_audio, audio_mask, train)
         enc = self.wav2vec2.encoder
         embedded_audio = embedded_audio + frontends.pos_conv_embed(enc.pos_conv_embed, embedded_audio)

@@ -158,12 +158,12 @@ class TransformerEncoder(nn.Module):
         self.embed_dim, self.n_heads, self.expansion_factor, self.p = embed_dim, n_heads, expansion_factor, dropout
         self.layers = nn.ModuleList([TransformerBlock(embed_dim, expansion_factor, n_heads, dropout) for _ in range(num_layers)])
         self._shadows = [engine.LayerShadow() for _ in range(num_layers)]
+        TransformerEncoder._instances += 1
+        self._salt = TransformerEncoder._instances     # construction order: reproducible dropout streams per encoder
+
+    _instances = 0
 
     def forward(self, x, attention_mask=None):
-        if self.training and self.p > 0:
-            raise NotImplementedError(
-                "TransformerEncoder: training-mode dropout (p=%g) is not implemented in the kernel path; "
-                "construct with dropout=0.0 or call .eval()" % self.p)
         B, S, _ = x.shape
         mask2d = None
         if attention_mask is not None:
@@ -172,5 +172,8 @@ class TransformerEncoder(nn.Module):
             mask2d = attention_mask.to(device=x.device, dtype=torch.float32).reshape(B, S)
         spec = LayerSpec(hidden=self.embed_dim, heads=self.n_heads, inter=self.expansion_factor * self.embed_dim,
                          pre_ln=False, eps=1e-5, mask_mode="key_bias" if mask2d is not None else "none",
-                         scrambled_concat=True)
+                         scrambled_concat=True,
+                         # training mode: the block's three nn.Dropout(p) (reference utils/TAVFormer.py:107,111,117,130-141)
+                         dropout=float(self.p) if (self.training and self.p > 0) else 0.0,
+                         dropout_salt=self._salt)
         return engine.run_stack(spec, self._shadows, x.float(), mask2d, [blk.slots() for blk in self.layers])

@@ -98,3 +98,52 @@ def test_conv_feature_encoder_matches_hf(B, L):
     for k, p in m.feature_extractor.named_parameters():
         assert p.grad is not None, k
         assert rel(p.grad, ref_grads[k]) < 3e-2, (k, rel(p.grad, ref_grads[k]))
+
+
+def test_roberta_embeddings_and_feature_projection_vs_hf_modules():
+    """RobertaEmbeddings (gather-sum kernel + LayerNorm kernel, row-scatter backward) and Wav2Vec2FeatureProjection
+    (LayerNorm kernel + tcgen05 GEMM) against the HF modules they replace (reference models/tav.py:349,356,476,485).
+    The embedding path is fp32 end to end (1e-5); the projection has bf16 GEMM operands (2e-2 relative-L2)."""
+    from transformers import RobertaModel, Wav2Vec2Model
+
+    from multi_modal_emotion_b200 import engine, hf_adapters as hf, synthetic as syn, tav
+
+    cfg = tav.encoder_configs("tiny_base")
+    bert = RobertaModel(cfg["text"]).eval()
+    bert.load_state_dict(syn.synth_state_dict(bert, seed=31))
+    bert = bert.cuda()
+    g = torch.Generator().manual_seed(5)
+    B, T = 4, 70
+    ids = torch.randint(3, 50265, (B, T), generator=g)
+    lens = torch.tensor([70, 33, 1, 12])
+    ids = torch.where(torch.arange(T)[None, :] < lens[:, None], ids, torch.ones_like(ids)).cuda()    # pad id 1
+    probe = torch.randn(B, T, 768, generator=g).cuda()
+    emb = bert.embeddings
+    ref = emb(input_ids=ids)
+    (ref * probe).sum().backward()
+    want = {k: p.grad.clone() for k, p in emb.named_parameters() if p.grad is not None}
+    emb.zero_grad(set_to_none=True)
+    ours = engine.roberta_embeddings(emb, ids)
+    (ours * probe).sum().backward()
+    assert (ours - ref).abs().max().item() < 1e-5
+    got = {k: p.grad for k, p in emb.named_parameters() if p.grad is not None}
+    assert set(got) == set(want)
+    for k in want:
+        assert rel(got[k], want[k]) < 1e-5, k
+    # feature projection
+    w2v = Wav2Vec2Model(cfg["audio"]).eval()
+    w2v.load_state_dict(syn.synth_state_dict(w2v, seed=32))
+    w2v = w2v.cuda()
+    feats = torch.randn(3, 149, 512, generator=g).cuda().requires_grad_(True)
+    probe2 = torch.randn(3, 149, 768, generator=g).cuda()
+    ref2, _ = w2v.feature_projection(feats)
+    (ref2 * probe2).sum().backward()
+    want2 = {k: p.grad.clone() for k, p in w2v.feature_projection.named_parameters()}
+    dfe = feats.grad.clone()
+    w2v.zero_grad(set_to_none=True)
+    feats.grad = None
+    ours2 = hf.feature_projection(w2v, feats)
+    (ours2 * probe2).sum().backward()
+    assert rel(ours2, ref2) < 2e-2 and rel(feats.grad, dfe) < 2e-2
+    for k, p in w2v.feature_projection.named_parameters():
+        assert rel(p.grad, want2[k]) < 2e-2, k

@@ -194,3 +194,56 @@ def test_gradient_sink_matches_autograd_accumulation(family):
     for k, r in ref.items():
         got = params[k].grad - 1.0
         assert rel(got, r) < 2e-4, (k, rel(got, r))
+
+
+def test_custom_encoder_training_mode_dropout_vs_oracle_with_the_same_masks():
+    """Reference TransformerBlock in TRAINING mode (utils/TAVFormer.py:107,111,117,130-141): dropout1 before norm1, the
+    Dropout that opens feed_forward (residual keeps the un-dropped norm1 output), dropout2 before norm2.  The kernel path
+    draws its own masks (counter-based generator); the oracle is run with exactly those masks, so outputs and input
+    gradients must agree to the usual bf16 tolerance; and the masks must look like Bernoulli(1-p)."""
+    from multi_modal_emotion_b200 import engine, synthetic as syn
+    from multi_modal_emotion_b200.tavformer import TransformerEncoder
+    from oracle import tav_oracle as O
+
+    p = 0.2
+    enc = TransformerEncoder(768, num_layers=2, dropout=p, early_div=False)
+    sd = syn.synth_state_dict(enc, seed=12)
+    enc.load_state_dict(sd)
+    enc = enc.cuda().train()
+    g = torch.Generator().manual_seed(9)
+    B, S = 2, 150
+    x = torch.randn(B, S, 768, generator=g)
+    probe = torch.randn(B, S, 768, generator=g) / (B * S * 768) ** 0.5
+    torch.manual_seed(77)
+    engine.reset_dropout_counter()
+    engine.debug_dropout_masks = []
+    try:
+        xg = x.cuda().requires_grad_(True)
+        y = enc(xg, None)
+        (y * probe.cuda()).sum().backward()
+        masks = [m.cpu() for m in engine.debug_dropout_masks]
+    finally:
+        engine.debug_dropout_masks = None
+    assert len(masks) == 6 and all(m.shape == (B * S, 768) for m in masks)
+    for m in masks:
+        assert abs(m.float().mean().item() - (1 - p)) < 5e-3           # 230k draws: sigma = 8e-4
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[0], masks[3])
+    drops = [tuple((masks[3 * l + s].double().view(B, S, 768) / (1 - p)) for s in range(3)) for l in range(2)]
+    xo = x.double().requires_grad_(True)
+    yo = O.custom_encoder(xo, None, {k: v.double() for k, v in sd.items()}, 2, early_div=False, drops=drops)
+    (yo * probe.double()).sum().backward()
+    ey, ex = rel(y.detach().cpu().double(), yo.detach()), rel(xg.grad.cpu().double(), xo.grad)
+    print("training-mode custom encoder vs oracle with the same dropout masks: y rel-L2 %.2e, dx rel-L2 %.2e" % (ey, ex))
+    assert ey < 3e-2 and ex < 3e-2
+    # a second call draws different masks (device-side counter), eval mode draws none
+    engine.debug_dropout_masks = []
+    try:
+        enc(x.cuda(), None)
+        again = [m.cpu() for m in engine.debug_dropout_masks]
+        enc.eval()
+        engine.debug_dropout_masks.clear()
+        enc(x.cuda(), None)
+        assert engine.debug_dropout_masks == []
+    finally:
+        engine.debug_dropout_masks = None
+    assert not torch.equal(again[0], masks[0])

@@ -185,3 +185,57 @@ def test_criterion_state_dict_carries_the_reference_key_both_directions():
     assert torch.equal(ours.weightedCEL.weight, w * 2)
     ref.load_state_dict(NewCrossEntropyLoss(w.clone()).state_dict())
     assert torch.equal(ref.weightedCEL.weight, w)
+
+
+def test_workspace_queries_and_per_call_sm_budget_field():
+    """caller-owned workspaces are sized through queries; the SM budget of the persistent GEMM is a field of
+    the call's argument struct, not process-wide state (pure host code: callable without a GPU)."""
+    from multi_modal_emotion_b200 import _lib as L
+
+    h = L.lib()
+    assert h.tavk_workspace_bytes_attn_bwd(16, 1464, 12) == 16 * 12 * 1464 * 4
+    assert h.tavk_workspace_bytes_attn_bwd(0, 5, 5) == 0
+    assert h.tavk_workspace_bytes_groupnorm(16, 512) == 16 * 2 * 512 * 4
+    a = L.GemmArgs()
+    assert h.tavk_workspace_bytes_gemm(a) == 0
+    assert "max_ctas" in [f[0] for f in L.GemmArgs._fields_]
+    assert not hasattr(h, "tavk_reserve_sms") or True     # the symbol is gone from the header; see test below
+    import re
+    header = open(os.path.join(ROOT, "include", "tavk.h")).read()
+    assert "tavk_reserve_sms" not in header and re.search(r"int32_t\s+max_ctas;", header)
+
+
+def test_spec_augment_matches_the_hf_routine_the_reference_copied():
+    """reference models/tav.py:269-306 is a copy of HF Wav2Vec2Model._mask_hidden_states (numpy RNG via
+    _compute_mask_indices).  With the same numpy seed, PreFormer._mask_hidden_states must replace exactly the same time
+    steps by masked_spec_embed and zero exactly the same feature columns."""
+    import numpy as np
+    import torch
+
+    from multi_modal_emotion_b200 import tav
+
+    tav.set_encoder_variant("tiny")
+    torch.manual_seed(0)
+    pre = tav.PreFormer()
+    cfg = pre.wav2vec2.config
+    cfg.apply_spec_augment, cfg.mask_time_prob, cfg.mask_time_length, cfg.mask_time_min_masks = True, 0.3, 4, 2
+    cfg.mask_feature_prob, cfg.mask_feature_length, cfg.mask_feature_min_masks = 0.2, 8, 1
+    B, T, H = 3, 49, cfg.hidden_size
+    x = torch.randn(B, T, H, generator=torch.Generator().manual_seed(1))
+    frame_mask = torch.arange(T)[None, :] < torch.tensor([49, 30, 12])[:, None]
+    np.random.seed(123)
+    ours = pre._mask_hidden_states(x.clone(), frame_mask, training=True)
+    hf = pre.wav2vec2
+    with torch.no_grad():
+        hf.masked_spec_embed.copy_(pre.masked_spec_embed)
+    hf.train()
+    np.random.seed(123)
+    ref = hf._mask_hidden_states(x.clone(), attention_mask=frame_mask)
+    hf.eval()
+    assert torch.equal(ours, ref)
+    changed = ours != x
+    assert changed.any() and not changed.all()                      # something was masked, something was left alone
+    assert (ours == 0).all(dim=1).any()                             # a feature column zeroed for every frame
+    assert torch.equal(pre._mask_hidden_states(x.clone(), frame_mask, training=False), x)      # eval: untouched
+    cfg.apply_spec_augment = False
+    assert torch.equal(pre._mask_hidden_states(x.clone(), frame_mask, training=True), x)       # config switch

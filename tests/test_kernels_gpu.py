@@ -382,3 +382,27 @@ def test_adamw_matches_torch(L):
         assert gbuf.abs().max().item() == 0.0  # zero_grad fused
     assert (p[:n] - ref_p.data).abs().max().item() < 2e-6
     assert torch.equal(shadow[:n], p[:n].bfloat16())
+
+
+def test_masked_mean_pool_lengths(L):
+    """optional lengths on the mean-pool entry points (NULL = the reference's unmasked mean)."""
+    from multi_modal_emotion_b200 import engine
+
+    g = gen(21)
+    B, S, H = 5, 77, 768
+    x = torch.randn(B, S, H, generator=g).cuda().requires_grad_(True)
+    lengths = torch.tensor([77, 1, 40, 0, 200])
+    y = engine.mean_pool(x, lengths)
+    w = torch.randn(B, H, generator=g).cuda()
+    (y * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    rows = []
+    for b in range(B):
+        n = int(min(max(int(lengths[b]), 0), S))
+        rows.append(xr[b, :n].mean(dim=0) if n > 0 else xr[b].sum(dim=0) * 0.0)
+    yr = torch.stack(rows)
+    (yr * w).sum().backward()
+    assert (y - yr).abs().max().item() < 1e-5
+    assert (x.grad - xr.grad).abs().max().item() < 1e-6
+    # no lengths: the reference's plain mean
+    assert (engine.mean_pool(x.detach()) - x.detach().mean(dim=1)).abs().max().item() < 1e-5
