@@ -176,10 +176,11 @@ int tavk_embed_add_bwd(const float* dy, const int64_t* idx, float* dtable, int r
  * non-pad tokens and pad_id for pad tokens; pos_ids (int64 [B,T]) receives p for the backward scatter. */
 int tavk_roberta_embed_fwd(const int64_t* ids, const float* word, const float* pos, const float* type0, float* y,
                            int64_t* pos_ids, int B, int T, int H, int vocab, int n_pos, int pad_id, void* stream);
-/* dtable[idx[r],:] += dy[r,:] for r < rows (idx outside [0,n_embed) skipped): embedding backward as a row scatter into a
+/* dtable[idx[r],:] += dy[r,:] for r < rows (idx outside [0,n_embed) and idx == skip_idx skipped; skip_idx = the
+ * nn.Embedding padding_idx, whose row receives no gradient, or -1): embedding backward as a row scatter into a
  * caller-owned (pre-zeroed or accumulating) table gradient. */
 int tavk_embedding_scatter_add(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed,
-                               void* stream);
+                               int skip_idx, void* stream);
 /* y[b,:] = (1/S) sum_s x[b,s,:]  — torch.mean(dim=1) at models/tav.py:478,481,488 (unmasked). */
 int tavk_mean_pool_fwd(const float* x, float* y, int B, int S, int H, void* stream);
 /* dx[b,s,:] = dy[b,:] / S ; also emits a bf16 copy when dx_bf16 != NULL. */

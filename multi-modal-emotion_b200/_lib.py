@@ -83,7 +83,7 @@ SIGNATURES = {
     "tavk_embed_add_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "tavk_embed_add_bwd": [_P, _P, _P, _I, _I, _I, _P],
     "tavk_roberta_embed_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "tavk_embedding_scatter_add": [_P, _P, _P, _I, _I, _I, _P],
+    "tavk_embedding_scatter_add": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tavk_mean_pool_fwd": [_P, _P, _I, _I, _I, _P],
     "tavk_mean_pool_bwd": [_P, _P, _P, _I, _I, _I, _P],
     "tavk_masked_mean_pool_fwd": [_P, _P, _P, _I, _I, _I, _P],

@@ -63,6 +63,7 @@ struct GemmDev {
     int epilogue;
     int accumulate;
     float alpha;
+    int tma_epi;                    // bf16 outputs leave through TMA stores (epilogue_loop_tma); see the host-side conditions
     int debug;                      // TAVK_GEMM_DEBUG (measurement only): 1 = drain TMEM and drop the tile, 2 = no global stores,
                                     // 3 = stores folded onto 128 rows (no DRAM write-back)
 };
@@ -338,10 +339,180 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
     }
 }
 
+// ---------------------------------------------------------------------------------------------- TMA-store epilogue
+// bf16 outputs without residual / row-bias (QKV, FFN-up + GELU, the FFN-up dgrad, attention-output dgrad, the conv
+// feature-encoder layers).  Measured on the coalesced-store epilogue above (TAVK_GEMM_DEBUG, profiles/r2_gemm_epilogue_*):
+// at M = 23424, N = 3072, K = 768 the main loop + TMEM drain takes 70 us, staging + GELU math 11 us more, and the st.global
+// instructions another 40 us even when they never reach DRAM — 8-byte-per-lane bf16 stores move 64-byte row pieces, and the
+// LSU path, not HBM, paces the epilogue.  Here the warps never issue a global store: everything elementwise happens in the
+// accumulator layout (lane = row, 32 consecutive columns in registers; bias arrives as warp-uniform loads), the bf16
+// rows go to a 2 KB SWIZZLE_64B patch (half the shared-memory traffic of the fp32 transpose patch) and one lane hands the
+// patch to the TMA unit, which writes full lines asynchronously and clips the M / N edges itself.  The GELU' multiplier
+// of TAVK_EPI_MUL / GELU_BWD comes in the same way (TMA load of the 32x32 bf16 box, one chunk ahead).
+TAVK_DEVINL uint32_t sw64_off(int row, int chunk16) {      // byte offset of 16-byte chunk `chunk16` of 64-byte row `row`
+    return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((chunk16 ^ ((row >> 1) & 3)) << 4));
+}
+
+template <int BLOCK_N, int MODE>
+TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2,
+                                   const CUtensorMap* tmap_aux, uint32_t tmem_base, uint8_t* stg, uint64_t* aux_bar, int lane,
+                                   int quarter, int half, int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+    constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
+    constexpr bool kGelu = (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD);
+    constexpr bool kAux = (MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL);
+    uint8_t* buf0 = stg;                    // out
+    uint8_t* buf1 = stg + 2048;             // out2 (GELU modes) | aux (MUL / GELU_BWD) | second out buffer (LINEAR)
+    auto coords = [&](int tile, int ci, int& row0, int& col0) {
+        const int mn = tile / p.k_splits;                    // k_splits == 1 on this path, groups == 1
+        const int m_blk = mn / p.num_n_blocks;
+        row0 = m_blk * kBlockM + quarter * 32;
+        col0 = (mn - m_blk * p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32;
+    };
+    int tile = blockIdx.x, ci = 0, it = 0, n_item = 0;
+    if (tile >= num_tiles) return;
+    int row0, col0;
+    coords(tile, 0, row0, col0);
+    uint32_t aux_phase = 0;
+    if (kAux && lane == 0) {
+        mbar_arrive_expect_tx(aux_bar, 2048);
+        tma_load_2d(buf1, tmap_aux, aux_bar, col0, row0);
+    }
+#pragma unroll 1
+    while (true) {
+        int ntile = tile, nci = ci + 1;
+        if (nci == kPer) { nci = 0; ntile += (int)gridDim.x; }
+        const bool more = ntile < num_tiles;
+        int nrow0 = 0, ncol0 = 0;
+        if (more) coords(ntile, nci, nrow0, ncol0);
+        // bias of the chunk's 32 columns: the same addresses in every lane (broadcast loads), issued before the waits
+        float bias[32];
+        if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 + 4 * j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);   // N % 8 == 0
+                bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bias[j] = 0.f;
+        }
+        const int acc = it & 1;
+        if (ci == 0) {
+            mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+        }
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + (half + 2 * ci) * 32), r);
+        tmem_ld_wait();
+        if (ci == kPer - 1) {
+            // last chunk of the tile for this warp: hand the TMEM buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            ++it;
+        }
+        if (p.debug == 1) {
+            if (!more) break;
+            tile = ntile; ci = nci; row0 = nrow0; col0 = ncol0;
+            continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias[j]);
+        uint32_t o[16], o2[16];
+        if (kAux) {
+            // this chunk's multiplier box has landed in buf1: read my row, then let the next box overwrite it
+            mbar_wait(aux_bar, aux_phase);
+            aux_phase ^= 1;
+            uint32_t a[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 t = ld_shared_v4(smem_u32(buf1) + sw64_off(lane, c));
+                a[4 * c] = __float_as_uint(t.x); a[4 * c + 1] = __float_as_uint(t.y);
+                a[4 * c + 2] = __float_as_uint(t.z); a[4 * c + 3] = __float_as_uint(t.w);
+            }
+            fence_proxy_async_shared();     // generic reads of buf1 before the async-proxy write of the next box
+            __syncwarp();
+            if (more && lane == 0) {
+                mbar_arrive_expect_tx(aux_bar, 2048);
+                tma_load_2d(buf1, tmap_aux, aux_bar, ncol0, nrow0);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float2 m2 = unpack_bf16x2(a[j]);
+                if (MODE == TAVK_EPI_MUL) {
+                    v[2 * j] *= m2.x; v[2 * j + 1] *= m2.y;
+                } else {
+                    gelu_grad_mul2(m2.x, m2.y, v[2 * j], v[2 * j + 1]);
+                }
+            }
+        }
+        if (kGelu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float g0, g1;
+                if (MODE == TAVK_EPI_GELU) {
+                    gelu_fast2(v[2 * j], v[2 * j + 1], g0, g1);
+                    o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                } else {
+                    float d0, d1;
+                    gelu_and_grad2(v[2 * j], v[2 * j + 1], g0, g1, d0, d1);
+                    o[j] = pack_bf16x2(d0, d1);
+                }
+                o2[j] = pack_bf16x2(g0, g1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
+        // staging buffers: LINEAR alternates buf0 / buf1 (one store may still be reading the other); the two-output and
+        // aux modes own one buffer per role and wait for the previous chunk's store to have read it
+        uint8_t* ob = (!kGelu && !kAux && (n_item & 1)) ? buf1 : buf0;
+        if (lane == 0) {
+            if (!kGelu && !kAux) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+        }
+        __syncwarp();
+        if (p.debug != 2) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                st_shared_v4(smem_u32(ob) + sw64_off(lane, c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+            if (kGelu) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    st_shared_v4(smem_u32(buf1) + sw64_off(lane, c), o2[4 * c], o2[4 * c + 1], o2[4 * c + 2], o2[4 * c + 3]);
+            }
+            fence_proxy_async_shared();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && col0 < p.N) {
+                tma_store_2d(tmap_out, ob, col0, row0);
+                if (kGelu) tma_store_2d(tmap_out2, buf1, col0, row0);
+                tma_store_commit();
+            }
+        }
+        if (!kGelu && p.colsum != nullptr) {
+            // column sums of the stored values (bias gradient of the Linear whose output gradient this GEMM produces)
+            if (row0 + lane >= p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            const float cs = warp_colsum32(v, lane);
+            if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
+        }
+        ++n_item;
+        if (!more) break;
+        tile = ntile; ci = nci; row0 = nrow0; col0 = ncol0;
+    }
+    if (lane == 0) tma_store_wait<0>();     // shared memory must outlive the last stores' reads; make them complete
+    __syncwarp();
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmDev p) {
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+                         const __grid_constant__ CUtensorMap tmap_aux, const GemmDev p) {
     using Cfg = GemmCfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -354,7 +525,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
     uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    uint64_t* aux_bar = bars + 2 * Cfg::kStages + 4;          // one per epilogue warp (TMA-store epilogue, aux boxes)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4 + kNumEpiWarps);
 
     const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -369,6 +541,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+        }
+        for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&tmap_out);
+            if (p.out2 != nullptr) tma_prefetch_desc(&tmap_out2);
+            if (p.aux != nullptr) tma_prefetch_desc(&tmap_aux);
         }
         mbar_fence_init();
     }
@@ -467,9 +645,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int quarter = warp_idx & 3;       // TMEM lane quarter this warp may access
         const int half = ew >> 2;               // which half of the column chunks
         const uint32_t stg = smem_u32(smem_stage) + ew * 4096;
+#define TAVK_EPI_TMA(MODE)                                                                                             \
+    epilogue_loop_tma<BLOCK_N, MODE>(p, &tmap_out, &tmap_out2, &tmap_aux, tmem_base, smem_stage + ew * 4096, &aux_bar[ew], lane, \
+                                     quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
 #define TAVK_EPI(MODE, OUT) \
     epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
-        if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI(TAVK_EPI_GELU, OUT_BF16);
+        if (p.tma_epi) {
+            if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI_TMA(TAVK_EPI_GELU);
+            else if (p.epilogue == TAVK_EPI_GELU_GRAD) TAVK_EPI_TMA(TAVK_EPI_GELU_GRAD);
+            else if (p.epilogue == TAVK_EPI_MUL) TAVK_EPI_TMA(TAVK_EPI_MUL);
+            else if (p.epilogue == TAVK_EPI_GELU_BWD) TAVK_EPI_TMA(TAVK_EPI_GELU_BWD);
+            else TAVK_EPI_TMA(TAVK_EPI_LINEAR);
+        } else if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI(TAVK_EPI_GELU, OUT_BF16);
         else if (p.epilogue == TAVK_EPI_GELU_GRAD) TAVK_EPI(TAVK_EPI_GELU_GRAD, OUT_BF16);
         else if (p.epilogue == TAVK_EPI_MUL) TAVK_EPI(TAVK_EPI_MUL, OUT_BF16);
         else if (p.epilogue == TAVK_EPI_GELU_BWD) TAVK_EPI(TAVK_EPI_GELU_BWD, OUT_BF16);
@@ -477,6 +664,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         else if (p.accumulate) TAVK_EPI(TAVK_EPI_LINEAR, OUT_RED);
         else TAVK_EPI(TAVK_EPI_LINEAR, OUT_F32);
 #undef TAVK_EPI
+#undef TAVK_EPI_TMA
     }
 
     tc_fence_before();
@@ -507,7 +695,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major matrix [rows, cols] (cols contiguous, row pitch ld elements).
 static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
-                          int box_rows) {
+                          int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode_fn();
     TAVK_CHECK(enc != nullptr, 3, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -515,7 +703,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TAVK_CHECK(r == CUDA_SUCCESS, 3, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d base=%p",
                (int)r, rows, cols, ld, box_cols, box_rows, base);
@@ -523,7 +711,8 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& dev, int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       const CUtensorMap& tx, const GemmDev& dev, int grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N>;
     auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
     static bool attr_done = false;
@@ -531,7 +720,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
         TAVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    TAVK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, dev));
+    TAVK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, to, to2, tx, dev));
     return 0;
 }
 
@@ -623,13 +812,35 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     else               rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, kBlockK, block_n);
     if (rc) return rc;
 
+    // TMA-store epilogue (see epilogue_loop_tma): plain bf16 outputs of one ungrouped problem
+    static const int tma_off = getenv("TAVK_GEMM_TMA_EPI") ? (atoi(getenv("TAVK_GEMM_TMA_EPI")) == 0) : 0;
+    d.tma_epi = (!tma_off && d.out_bf16 && d.groups == 1 && d.k_splits == 1 && !a->accumulate && a->resid == nullptr &&
+                 a->rowbias == nullptr && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->ldo % 8 == 0 &&
+                 (a->out2 == nullptr || ((reinterpret_cast<uintptr_t>(a->out2) & 15) == 0 && a->ldo2 % 8 == 0)) &&
+                 (a->aux == nullptr || ((reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->ldaux % 8 == 0)) &&
+                 (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0))
+                    ? 1 : 0;
+    CUtensorMap to = ta, to2 = ta, tx = ta;      // placeholders when unused (never dereferenced)
+    if (d.tma_epi) {
+        rc = make_tmap_bf16(&to, a->out, a->M, a->N, a->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        if (a->out2 != nullptr) {
+            rc = make_tmap_bf16(&to2, a->out2, a->M, a->N, a->ldo2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        }
+        if (epi_aux) {
+            rc = make_tmap_bf16(&tx, a->aux, a->M, a->N, a->ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        }
+    }
+
     const long long tiles = (long long)d.groups * d.tiles_per_group;
     const int grid = (int)(tiles < sms ? tiles : sms);
 #define TAVK_GEMM_DISPATCH(BN)                                                                   \
-    if (a->a_mn_major && a->b_mn_major) return launch_gemm<BN, true, true>(ta, tb, d, grid, stream);   \
-    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN, true, false>(ta, tb, d, grid, stream); \
-    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN, false, true>(ta, tb, d, grid, stream); \
-    return launch_gemm<BN, false, false>(ta, tb, d, grid, stream);
+    if (a->a_mn_major && a->b_mn_major) return launch_gemm<BN, true, true>(ta, tb, to, to2, tx, d, grid, stream);   \
+    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN, true, false>(ta, tb, to, to2, tx, d, grid, stream); \
+    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN, false, true>(ta, tb, to, to2, tx, d, grid, stream); \
+    return launch_gemm<BN, false, false>(ta, tb, to, to2, tx, d, grid, stream);
     if (block_n == 256) { TAVK_GEMM_DISPATCH(256) }
     if (block_n == 128) { TAVK_GEMM_DISPATCH(128) }
     TAVK_GEMM_DISPATCH(64)

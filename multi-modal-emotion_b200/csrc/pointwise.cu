@@ -81,14 +81,14 @@ roberta_embed_fwd_kernel(const int64_t* __restrict__ ids, const float4* __restri
 // dtable[idx[r], :] += dy[r, :]  (row scatter with vector reductions; the table gradient is never materialised densely
 // by this call: it accumulates into whatever buffer the caller owns, e.g. the parameter's slice of the flat gradient)
 __global__ void embedding_scatter_add_kernel(const float* __restrict__ dy, const int64_t* __restrict__ idx,
-                                             float* __restrict__ dtable, int rows, int H4, int n_embed) {
+                                             float* __restrict__ dtable, int rows, int H4, int n_embed, int skip_idx) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
     const long long total = (long long)rows * H4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / H4), c = (int)(i - (long long)r * H4);
         const long long j = idx[r];
-        if (j < 0 || j >= n_embed) continue;
+        if (j < 0 || j >= n_embed || j == skip_idx) continue;     // nn.Embedding(padding_idx=...): that row gets no gradient
         const float4 v = reinterpret_cast<const float4*>(dy)[i];
         float* o = dtable + ((size_t)j * H4 + c) * 4;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -482,7 +482,7 @@ extern "C" int tavk_roberta_embed_fwd(const int64_t* ids, const float* word, con
 }
 
 extern "C" int tavk_embedding_scatter_add(const float* dy, const int64_t* idx, float* dtable, int rows, int H, int n_embed,
-                                          void* stream) {
+                                          int skip_idx, void* stream) {
     TAVK_CHECK(dy && idx && dtable, 1, "tavk_embedding_scatter_add: null pointer");
     TAVK_CHECK(H % 4 == 0, 1, "tavk_embedding_scatter_add: H=%d must be a multiple of 4", H);
     TAVK_CHECK(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dtable)) & 15) == 0, 1,
@@ -490,7 +490,7 @@ extern "C" int tavk_embedding_scatter_add(const float* dy, const int64_t* idx, f
     if (rows <= 0) return 0;
     const long long total = (long long)rows * (H / 4);
     TAVK_CUDA(launch_kernel(embedding_scatter_add_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), STREAM(stream), dy, idx, dtable,
-                            rows, H / 4, n_embed));
+                            rows, H / 4, n_embed, skip_idx));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -597,7 +597,7 @@ class _RobertaEmbedFn(torch.autograd.Function):
     written and added as three dense passes."""
 
     @staticmethod
-    def forward(ctx, ids, word, pos, typ, pad_id):
+    def forward(ctx, ids, word, pos, typ, pad_id, pads):
         B, T = ids.shape
         V, H = word.shape
         ids = ids.contiguous().long()
@@ -607,6 +607,7 @@ class _RobertaEmbedFn(torch.autograd.Function):
                pos_ids.data_ptr(), B, T, H, V, pos.shape[0], int(pad_id))
         ctx.save_for_backward(ids, pos_ids)
         ctx.tables = (word, pos, typ)
+        ctx.pads = pads
         return y
 
     @staticmethod
@@ -617,7 +618,8 @@ class _RobertaEmbedFn(torch.autograd.Function):
         H = word.shape[1]
         dy = dy.contiguous().float()
         outs, written = [], []
-        for table, idx, need in ((word, ids, ctx.needs_input_grad[1]), (pos, pos_ids, ctx.needs_input_grad[2])):
+        for table, idx, need, skip in ((word, ids, ctx.needs_input_grad[1], ctx.pads[0]),
+                                       (pos, pos_ids, ctx.needs_input_grad[2], ctx.pads[1])):
             if not need:
                 outs.append(None)
                 continue
@@ -628,7 +630,8 @@ class _RobertaEmbedFn(torch.autograd.Function):
             else:
                 outs.append(None)
                 written.append(table)
-            L.call("tavk_embedding_scatter_add", dy.data_ptr(), idx.data_ptr(), g.data_ptr(), B * T, H, table.shape[0])
+            L.call("tavk_embedding_scatter_add", dy.data_ptr(), idx.data_ptr(), g.data_ptr(), B * T, H, table.shape[0],
+                   -1 if skip is None else int(skip))
         dtyp = None
         if ctx.needs_input_grad[3]:
             g = _sink(typ)
@@ -641,7 +644,7 @@ class _RobertaEmbedFn(torch.autograd.Function):
             L.colsum(dy.view(B * T, H), colsum_target, M=B * T, N=H, accumulate=True)
         if grad_written_hook is not None and written:
             grad_written_hook(written)
-        return None, outs[0], outs[1], dtyp, None
+        return None, outs[0], outs[1], dtyp, None, None
 
 
 def roberta_embeddings(emb, input_ids):
@@ -649,8 +652,10 @@ def roberta_embeddings(emb, input_ids):
     kernel, then the LayerNorm kernel (dropout: the HF sub-models stay in eval mode)."""
     if emb.training and emb.dropout.p > 0:
         raise NotImplementedError("RobertaEmbeddings dropout in training mode (the reference keeps the HF models in eval)")
+    # nn.Embedding(padding_idx=...) rows receive no gradient: word and position tables both carry one in HF RoBERTa
     x = _RobertaEmbedFn.apply(input_ids, emb.word_embeddings.weight, emb.position_embeddings.weight,
-                              emb.token_type_embeddings.weight, emb.padding_idx)
+                              emb.token_type_embeddings.weight, emb.padding_idx,
+                              (emb.word_embeddings.padding_idx, emb.position_embeddings.padding_idx))
     return layer_norm(x, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
 
 

@@ -67,10 +67,11 @@ def test_tav_baseline_families_vs_oracle(cfg, B):
     assert torch.equal(logits.argmax(dim=1)[sure], lo.argmax(dim=1)[sure])
     assert set(og) == set(grads), "the same parameters receive gradients as in the oracle"
     gmax = max(g.norm().item() for g in og.values())
-    worst, num, den, bad = ("", 0.0), 0.0, 0.0, []
+    worst, num, den, bad, contrib = ("", 0.0), 0.0, 0.0, [], []
     for k, go in og.items():
         d2, n2 = (grads[k].cpu() - go).norm().item() ** 2, go.norm().item() ** 2
         num, den = num + d2, den + n2
+        contrib.append((d2, n2, k))
         if n2 ** 0.5 < 1e-6 * gmax:
             continue  # below the oracle's own fp32 resolution (late fusion-layer q/k weights under Q1/Q2)
         e = (d2 / n2) ** 0.5
@@ -81,5 +82,7 @@ def test_tav_baseline_families_vs_oracle(cfg, B):
             bad.append((k, e, n2 ** 0.5))
     print("worst full-gradient rel-L2 %.3e at %s (%d tensors); whole-model flat gradient rel-L2 %.3e" % (
         worst[1], worst[0], len(og), (num / den) ** 0.5))
+    for d2, n2, k in sorted(contrib, reverse=True)[:4]:
+        print("   largest error contributions: %-70s |d| %.3e  |g| %.3e" % (k, d2 ** 0.5, n2 ** 0.5))
     assert not bad, bad
     assert (num / den) ** 0.5 < 2e-2

@@ -406,3 +406,41 @@ def test_masked_mean_pool_lengths(L):
     assert (x.grad - xr.grad).abs().max().item() < 1e-6
     # no lengths: the reference's plain mean
     assert (engine.mean_pool(x.detach()) - x.detach().mean(dim=1)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 136, 200), (129, 72, 64), (5168, 768, 768)])
+def test_gemm_tma_store_epilogue_edges(L, M, N, K):
+    """bf16 outputs leave through TMA stores (csrc/gemm_tcgen05.cu epilogue_loop_tma): ragged M / N edges are clipped by
+    the TMA unit, bias arrives as broadcast loads, the GELU' multiplier as TMA-loaded boxes; checked against torch and
+    against the coalesced-store epilogue (TAVK_GEMM_TMA_EPI=0 is read once per process, so the reference here is torch)."""
+    g = gen(31)
+    A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    acc = A.float() @ W.float().t()
+    guard = 7.0     # rows / columns past the edges must stay untouched
+    out = torch.full((M + 3, N + 8), guard, device="cuda", dtype=torch.bfloat16)
+    L.gemm(A, W, out, M=M, N=N, K=K, bias=bias, alpha=0.5, ldo=N + 8)
+    assert rel_l2(out[:M, :N], 0.5 * acc + bias) < 4e-3
+    assert (out[M:] == guard).all() and (out[:, N:] == guard).all()
+    dg = torch.full((M + 3, N + 8), guard, device="cuda", dtype=torch.bfloat16)
+    act = torch.full((M + 3, N + 8), guard, device="cuda", dtype=torch.bfloat16)
+    L.gemm(A, W, dg, M=M, N=N, K=K, bias=bias, out2=act, epilogue=L.EPI_GELU_GRAD, ldo=N + 8)
+    xe = (acc + bias).requires_grad_(True)
+    torch.nn.functional.gelu(xe).backward(torch.ones_like(xe))
+    assert rel_l2(act[:M, :N], torch.nn.functional.gelu(acc + bias)) < 4e-3
+    assert rel_l2(dg[:M, :N], xe.grad) < 4e-3
+    assert (dg[M:] == guard).all() and (act[:, N:] == guard).all()
+    aux = dg[:M, :N].contiguous()
+    outm = torch.full((M + 3, N), guard, device="cuda", dtype=torch.bfloat16)
+    cs = torch.full((N,), 3.0, device="cuda")
+    L.gemm(A, W, outm, M=M, N=N, K=K, aux=aux, epilogue=L.EPI_MUL, colsum=cs)
+    assert rel_l2(outm[:M], acc * aux.float()) < 4e-3
+    assert rel_l2(cs, 3.0 + (acc * aux.float()).sum(dim=0)) < 3e-3
+    assert (outm[M:] == guard).all()
+    pre = (acc + bias).bfloat16()
+    outg = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    L.gemm(A, W, outg, M=M, N=N, K=K, aux=pre, epilogue=L.EPI_GELU_BWD)
+    xp = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(xp).backward(torch.ones_like(xp))
+    assert rel_l2(outg, acc * xp.grad) < 4e-3
