@@ -245,6 +245,16 @@ int tavk_groupnorm_gelu_fwd(const void* u_bf16, const float* gamma, const float*
 int tavk_groupnorm_bwd(const void* dz_bf16, const void* u_bf16, const float* mean, const float* rstd,
                        const float* gamma, void* du_bf16, float* sums_ws, int B, int R, int T, int C, void* stream);
 int tavk_wave_windows(const float* wav, void* win_bf16, int B, int L, int R, int T, int k, int s, void* stream);
+/* Layer-norm family of the same encoder (HF Wav2Vec2LayerNormConvLayer: Conv1d + bias -> LayerNorm over the C channels ->
+ * GELU; the wav2vec2-large checkpoints the reference names, models/tav.py:257,455).  Channels-last bf16 [B, R, C] rows,
+ * C % 256 == 0, C <= 1024:
+ *   chan_ln_gelu_fwd : a = gelu_erf(gamma*(u-mean)*rstd + beta) per row; mean/rstd f32 [B*R] saved; padding rows zero
+ *   chan_ln_gelu_bwd : du = LN'(gelu'(z)*da) (z recomputed), dgamma/dbeta accumulated (f32 [C], atomics) */
+int tavk_chan_ln_gelu_fwd(const void* u_bf16, const float* gamma, const float* beta, void* a_bf16, float* mean, float* rstd,
+                          int B, int R, int T, int C, float eps, void* stream);
+int tavk_chan_ln_gelu_bwd(const void* da_bf16, const void* u_bf16, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, void* du_bf16, float* dgamma, float* dbeta, int B, int R, int T, int C,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Weighted softmax cross-entropy (utils/global_functions.py:63-64,76,83 — nn.CrossEntropyLoss(weight=w), mean).

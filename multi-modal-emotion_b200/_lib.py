@@ -103,6 +103,8 @@ SIGNATURES = {
     "tavk_groupnorm_gelu_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tavk_groupnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tavk_wave_windows": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "tavk_chan_ln_gelu_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tavk_chan_ln_gelu_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tavk_softmax_ce_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_softmax_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "tavk_grad_sqnorm": [_P, _L, _P, _P],

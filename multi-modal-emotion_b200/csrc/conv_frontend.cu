@@ -245,6 +245,147 @@ groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bflo
     }
 }
 
+// ---- layer-norm family (HF Wav2Vec2LayerNormConvLayer: Conv1d + bias -> LayerNorm over the C channels -> GELU; the
+// wav2vec2-large feature encoder the reference actually loads, models/tav.py:257,455) ------------------------------
+// One warp per (b, t) row of the channels-last activations [B, R, C], C % 256 == 0, C <= 1024: lane holds C/32 values as
+// 16-byte groups of 8 bf16; fp32 statistics (two-pass in registers); rows t >= T are padding (written as zeros).
+constexpr int kLnGMaxGroups = 4;
+__global__ void __launch_bounds__(256)
+chan_ln_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        __nv_bfloat16* __restrict__ a, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+                        int R, int T, int C, float eps) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    const int lane = threadIdx.x & 31;
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int ng = C >> 8;
+    const bool pad = (int)(row % R) >= T;
+    float x[kLnGMaxGroups][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < kLnGMaxGroups; ++g) {
+        if (g < ng) {
+            const uint4 q = *reinterpret_cast<const uint4*>(u + row * C + (g * 32 + lane) * 8);
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf16x2(w4[i]);
+                x[g][2 * i] = f.x; x[g][2 * i + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mu = warp_sum(sum) / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int g = 0; g < kLnGMaxGroups; ++g)
+        if (g < ng)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = x[g][i] - mu; var += d * d; }
+    const float rs = rsqrtf(warp_sum(var) / (float)C + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int g = 0; g < kLnGMaxGroups; ++g) {
+        if (g < ng) {
+            const int c0 = (g * 32 + lane) * 8;
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float z0 = (x[g][2 * i] - mu) * rs * __ldg(gamma + c0 + 2 * i) + __ldg(beta + c0 + 2 * i);
+                const float z1 = (x[g][2 * i + 1] - mu) * rs * __ldg(gamma + c0 + 2 * i + 1) + __ldg(beta + c0 + 2 * i + 1);
+                o[i] = pad ? 0u : pack_bf16x2(gelu_erf(z0), gelu_erf(z1));
+            }
+            *reinterpret_cast<uint4*>(a + row * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+// du = LN'(gelu'(z) * da) with z recomputed from (u, mean, rstd); dgamma += sum dz*xhat, dbeta += sum dz (block-level
+// reduction, one atomic per channel per block); du is zero in the padding rows
+__global__ void __launch_bounds__(256)
+chan_ln_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ u,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ du, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, long long rows, int R, int T, int C, int rows_per_warp) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    extern __shared__ float s_red[];        // [2][C] block partial sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ng = C >> 8;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+    float dg[kLnGMaxGroups][8], db[kLnGMaxGroups][8];
+#pragma unroll
+    for (int g = 0; g < kLnGMaxGroups; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dg[g][i] = 0.f; db[g][i] = 0.f; }
+    const long long row0 = ((long long)blockIdx.x * nwarps + warp) * rows_per_warp;
+    for (int rr = 0; rr < rows_per_warp; ++rr) {
+        const long long row = row0 + rr;
+        if (row >= rows) break;
+        const bool pad = (int)(row % R) >= T;
+        if (pad) {
+#pragma unroll
+            for (int g = 0; g < kLnGMaxGroups; ++g)
+                if (g < ng) *reinterpret_cast<uint4*>(du + row * C + (g * 32 + lane) * 8) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const float mu = mean[row], rs = rstd[row];
+        float xh[kLnGMaxGroups][8], dzg[kLnGMaxGroups][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < kLnGMaxGroups; ++g) {
+            if (g < ng) {
+                const int c0 = (g * 32 + lane) * 8;
+                const uint4 qu = *reinterpret_cast<const uint4*>(u + row * C + c0);
+                const uint4 qa = *reinterpret_cast<const uint4*>(da + row * C + c0);
+                const uint32_t wu[4] = {qu.x, qu.y, qu.z, qu.w}, wa[4] = {qa.x, qa.y, qa.z, qa.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 fu = unpack_bf16x2(wu[i]), fa = unpack_bf16x2(wa[i]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = 2 * i + h;
+                        const float gm = __ldg(gamma + c0 + e);
+                        const float xhat = ((h ? fu.y : fu.x) - mu) * rs;
+                        const float z = xhat * gm + __ldg(beta + c0 + e);
+                        const float dz = (h ? fa.y : fa.x) * gelu_erf_grad(z);
+                        xh[g][e] = xhat;
+                        dzg[g][e] = dz * gm;
+                        dg[g][e] += dz * xhat;
+                        db[g][e] += dz;
+                        s1 += dzg[g][e];
+                        s2 += dzg[g][e] * xhat;
+                    }
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+        for (int g = 0; g < kLnGMaxGroups; ++g) {
+            if (g < ng) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    o[i] = pack_bf16x2(rs * (dzg[g][2 * i] - s1 - xh[g][2 * i] * s2), rs * (dzg[g][2 * i + 1] - s1 - xh[g][2 * i + 1] * s2));
+                *reinterpret_cast<uint4*>(du + row * C + (g * 32 + lane) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kLnGMaxGroups; ++g)
+        if (g < ng)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                atomicAdd(&s_red[(g * 32 + lane) * 8 + i], dg[g][i]);
+                atomicAdd(&s_red[C + (g * 32 + lane) * 8 + i], db[g][i]);
+            }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(dgamma + i, s_red[i]);
+        atomicAdd(dbeta + i, s_red[C + i]);
+    }
+}
+
 // win[b*R + t, j] = bf16(wav[b, s*t + j]) for j < k (0 for k <= j < 16 and for rows t >= T): the B operand of the conv0
 // weight-gradient GEMM
 __global__ void wave_windows_kernel(const float* __restrict__ wav, __nv_bfloat16* __restrict__ win, int L, int R, int T,
@@ -310,6 +451,38 @@ extern "C" int tavk_groupnorm_bwd(const void* dz, const void* u, const float* me
     TAVK_CUDA(launch_kernel(groupnorm_bwd_apply_kernel, dim3(g2), dim3(256), (size_t)(0), stream, reinterpret_cast<const __nv_bfloat16*>(dz),
                                                        reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, gamma, sums_ws,
                                                        reinterpret_cast<__nv_bfloat16*>(du), R, T, C));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_chan_ln_gelu_fwd(const void* u, const float* gamma, const float* beta, void* a, float* mean, float* rstd,
+                                     int B, int R, int T, int C, float eps, void* stream) {
+    TAVK_CHECK(u && gamma && beta && a && mean && rstd, 1, "tavk_chan_ln_gelu_fwd: null pointer");
+    TAVK_CHECK(C % 256 == 0 && C <= 256 * kLnGMaxGroups && R >= T && T >= 0, 2, "tavk_chan_ln_gelu_fwd: unsupported shape C=%d R=%d T=%d", C, R, T);
+    const long long rows = (long long)B * R;
+    if (rows <= 0) return 0;
+    const long long blocks = (rows * 32 + 255) / 256;
+    TAVK_CUDA(launch_kernel(chan_ln_gelu_fwd_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, reinterpret_cast<cudaStream_t>(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(u), gamma, beta, reinterpret_cast<__nv_bfloat16*>(a), mean, rstd,
+                            rows, R, T, C, eps));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tavk_chan_ln_gelu_bwd(const void* da, const void* u, const float* mean, const float* rstd, const float* gamma,
+                                     const float* beta, void* du, float* dgamma, float* dbeta, int B, int R, int T, int C,
+                                     void* stream) {
+    TAVK_CHECK(da && u && mean && rstd && gamma && beta && du && dgamma && dbeta, 1, "tavk_chan_ln_gelu_bwd: null pointer");
+    TAVK_CHECK(C % 256 == 0 && C <= 256 * kLnGMaxGroups && R >= T && T >= 0, 2, "tavk_chan_ln_gelu_bwd: unsupported shape C=%d R=%d T=%d", C, R, T);
+    const long long rows = (long long)B * R;
+    if (rows <= 0) return 0;
+    const int rows_per_warp = 8;
+    const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
+    const long long blocks = (warps + 7) / 8;
+    TAVK_CUDA(launch_kernel(chan_ln_gelu_bwd_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(2 * C * sizeof(float)),
+                            reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(da),
+                            reinterpret_cast<const __nv_bfloat16*>(u), mean, rstd, gamma, beta, reinterpret_cast<__nv_bfloat16*>(du),
+                            dgamma, dbeta, rows, R, T, C, rows_per_warp));
     TAVK_CUDA(cudaGetLastError());
     return 0;
 }

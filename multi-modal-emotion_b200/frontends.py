@@ -19,10 +19,6 @@ import torch.nn.functional as F
 from . import _lib as L
 from .engine import _wgrad
 
-# Layer-norm feature encoders (wav2vec2-large family: Conv1d+bias -> LayerNorm -> GELU per layer) still run in cuDNN
-# under bf16 autocast; the group-norm family (wav2vec2-base, the benchmark workload) runs on the kernel library.
-FE_AUTOCAST = True
-
 
 def _fe_rows(L, kernels, strides):
     """Valid frames T_l per layer and padded rows-per-sample R_l with R_{l-1} = stride_l * R_l (and s_0 * R_0 >= L):
@@ -137,26 +133,125 @@ class _ConvFeatureEncoderFn(torch.autograd.Function):
         return (None, dgw, dgb, None, None, None, *grads)
 
 
+def _regroup_taps_bf16(w, st, d, k):
+    """conv weight [C_out, C_in, k] -> bf16 [st*C_in, d*C_out]: B operand of the dgrad GEMM that writes `st` input rows per
+    output row (taps regrouped by input phase r and delay dd; see _ConvFeatureEncoderFn)."""
+    C = w.shape[0]
+    b2 = torch.zeros((st, C, d, C), dtype=torch.bfloat16, device=w.device)
+    for r in range(st):
+        for dd in range(d):
+            tap = r + st * dd
+            if tap < k:
+                b2[r, :, d - 1 - dd, :].copy_(w[:, :, tap].t())
+    return b2.view(st * C, d * C)
+
+
+class _ConvFeatureEncoderLNFn(torch.autograd.Function):
+    """HF Wav2Vec2FeatureEncoder with feat_extract_norm="layer" (conv bias, LayerNorm over channels, GELU per layer — the
+    wav2vec2-large family the reference loads, models/tav.py:257,455) in the same channels-last / padded-row layout as
+    _ConvFeatureEncoderFn: layer 0 is the streaming conv kernel, every later Conv1d + bias is one tcgen05 GEMM with
+    overlapping TMA rows (bf16 output through the TMA-store epilogue), and LayerNorm + GELU is one warp-per-row kernel
+    (csrc/conv_frontend.cu chan_ln_gelu_*).  Backward per layer: LN'/GELU' kernel (z recomputed), conv-bias gradient as a
+    column sum, wgrad GEMM, dgrad GEMM writing `stride` input rows per output row."""
+
+    @staticmethod
+    def forward(ctx, wav, eps, kernels, strides, *params):
+        L.require_device()
+        n = len(kernels)
+        ws, bs, gs, bes = params[0:n], params[n:2 * n], params[2 * n:3 * n], params[3 * n:4 * n]
+        B, Ls = wav.shape
+        C = ws[0].shape[0]
+        dev = wav.device
+        T, R = _fe_rows(Ls, kernels, strides)
+        wav = wav.contiguous().float()
+        pad = 8
+        us = [torch.empty((B * R[l], C), dtype=torch.bfloat16, device=dev) for l in range(n)]
+        acts = [torch.zeros((B * R[l] + pad, C), dtype=torch.bfloat16, device=dev) for l in range(n)]
+        means = [torch.empty((B * R[l],), dtype=torch.float32, device=dev) for l in range(n)]
+        rstds = [torch.empty((B * R[l],), dtype=torch.float32, device=dev) for l in range(n)]
+        L.call("tavk_conv0_fwd", wav.data_ptr(), ws[0].data_ptr(), bs[0].data_ptr(), us[0].data_ptr(), B, Ls, R[0], T[0], C,
+               kernels[0], strides[0])
+        for l in range(n):
+            if l >= 1:
+                k, st = kernels[l], strides[l]
+                wk = L.cast_bf16(ws[l].detach().permute(0, 2, 1).contiguous().view(C, k * C))
+                L.gemm(acts[l - 1], wk, us[l], M=B * R[l], N=C, K=k * C, lda=st * C, bias=bs[l])
+            L.call("tavk_chan_ln_gelu_fwd", us[l].data_ptr(), gs[l].data_ptr(), bes[l].data_ptr(), acts[l].data_ptr(),
+                   means[l].data_ptr(), rstds[l].data_ptr(), B, R[l], T[l], C, float(eps))
+        ctx.save_for_backward(wav, *params, *us, *acts[:-1], *means, *rstds)
+        ctx.meta = (B, Ls, C, n, T, R, tuple(kernels), tuple(strides))
+        return acts[-1][:B * R[-1]].view(B, R[-1], C)[:, :T[-1]].float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Ls, C, n, T, R, kernels, strides = ctx.meta
+        sv = ctx.saved_tensors
+        wav = sv[0]
+        ws, bs, gs, bes = sv[1:1 + n], sv[1 + n:1 + 2 * n], sv[1 + 2 * n:1 + 3 * n], sv[1 + 3 * n:1 + 4 * n]
+        o = 1 + 4 * n
+        us, acts = sv[o:o + n], sv[o + n:o + 2 * n - 1]
+        means, rstds = sv[o + 2 * n - 1:o + 3 * n - 1], sv[o + 3 * n - 1:o + 4 * n - 1]
+        dev = dy.device
+        D = [-(-kernels[l] // strides[l]) for l in range(n)]
+        da = torch.zeros((B * R[-1], C), dtype=torch.bfloat16, device=dev)
+        da.view(B, R[-1], C)[:, :T[-1]].copy_(dy)
+        dws, dbs, dgs, dbes = [None] * n, [None] * n, [None] * n, [None] * n
+        for l in range(n - 1, -1, -1):
+            M = B * R[l]
+            lead = D[l] - 1 if l >= 1 else 0
+            du = torch.zeros((lead + M, C), dtype=torch.bfloat16, device=dev)     # leading zero rows: dgrad row windows
+            dgs[l] = torch.zeros((C,), dtype=torch.float32, device=dev)
+            dbes[l] = torch.zeros((C,), dtype=torch.float32, device=dev)
+            L.call("tavk_chan_ln_gelu_bwd", da.data_ptr(), us[l].data_ptr(), means[l].data_ptr(), rstds[l].data_ptr(),
+                   gs[l].data_ptr(), bes[l].data_ptr(), du[lead:].data_ptr(), dgs[l].data_ptr(), dbes[l].data_ptr(), B,
+                   R[l], T[l], C)
+            dbs[l] = torch.empty((C,), dtype=torch.float32, device=dev)
+            L.colsum(du[lead:], dbs[l], M=M, N=C)
+            if l == 0:
+                break
+            k, st, d = kernels[l], strides[l], D[l]
+            dwk = torch.zeros((C, k * C), dtype=torch.float32, device=dev)
+            tiles = ((C + 127) // 128) * ((k * C + 255) // 256)
+            ks = max(1, min(148 // tiles, (M + 511) // 512))
+            L.gemm(du[lead:], acts[l - 1], dwk, M=C, N=k * C, K=M, lda=C, ldb=st * C, a_mn=True, b_mn=True, accumulate=True,
+                   k_splits=ks)
+            dws[l] = dwk.view(C, k, C).permute(0, 2, 1)
+            da = torch.empty((B * R[l - 1], C), dtype=torch.bfloat16, device=dev)
+            L.gemm(du, _regroup_taps_bf16(ws[l].detach(), st, d, k), da.view(M, st * C), M=M, N=st * C, K=d * C, lda=C)
+        # layer 0: conv weight gradient = wgrad GEMM of du0 against the waveform's window matrix
+        k0, s0 = kernels[0], strides[0]
+        M0 = B * R[0]
+        win = torch.empty((M0, 16), dtype=torch.bfloat16, device=dev)
+        L.call("tavk_wave_windows", wav.data_ptr(), win.data_ptr(), B, Ls, R[0], T[0], k0, s0)
+        dw0 = torch.zeros((C, 16), dtype=torch.float32, device=dev)
+        L.gemm(du, win, dw0, M=C, N=16, K=M0, lda=C, ldb=16, a_mn=True, b_mn=True, accumulate=True,
+               k_splits=max(1, min(148 // ((C + 127) // 128), (M0 + 2047) // 2048)))
+        dws[0] = dw0[:, :k0].reshape(ws[0].shape)
+        return (None, None, None, None, *dws, *dbs, *dgs, *dbes)
+
+
 def feature_extractor_cl(w2v, wav):
-    """HF Wav2Vec2FeatureEncoder.forward in channels-last form: [B, L] -> [B, frames, C] (fp32)."""
+    """HF Wav2Vec2FeatureEncoder.forward in channels-last form: [B, L] -> [B, frames, C] (fp32), both norm families on
+    the kernel library (there is no cuDNN / autocast fallback: unsupported configurations raise)."""
     fe = w2v.feature_extractor
     c = w2v.config
     layers = fe.conv_layers
-    if (c.feat_extract_norm == "group" and not c.conv_bias and c.feat_extract_activation == "gelu" and wav.is_cuda
-            and max(c.conv_kernel) <= 16 and layers[0].conv.weight.shape[0] % 16 == 0
-            and len(set(l.conv.weight.shape[0] for l in layers)) == 1):
+    if not wav.is_cuda:
+        raise RuntimeError("the Wav2Vec2 feature encoder runs on the sm_100a kernel path only (no CPU fallback)")
+    same_c = len(set(l.conv.weight.shape[0] for l in layers)) == 1
+    C = layers[0].conv.weight.shape[0]
+    if c.feat_extract_activation != "gelu" or max(c.conv_kernel) > 16 or not same_c:
+        raise NotImplementedError("Wav2Vec2 feature encoder: GELU, kernels <= 16 and one channel count expected")
+    if c.feat_extract_norm == "group" and not c.conv_bias and C % 16 == 0:
         gn = layers[0].layer_norm
         return _ConvFeatureEncoderFn.apply(wav, gn.weight, gn.bias, gn.eps, tuple(c.conv_kernel), tuple(c.conv_stride),
                                            *[l.conv.weight for l in layers])
-    return feature_extractor(w2v, wav).transpose(1, 2)
-
-
-def feature_extractor(w2v, wav):
-    """HF Wav2Vec2FeatureEncoder.forward: [B, L] -> [B, C, frames] (fp32 out) through cuDNN (layer-norm family)."""
-    if FE_AUTOCAST and wav.is_cuda:
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            return w2v.feature_extractor(wav).float()
-    return w2v.feature_extractor(wav)
+    if c.feat_extract_norm == "layer" and c.conv_bias and C % 256 == 0 and C <= 1024:
+        return _ConvFeatureEncoderLNFn.apply(wav, layers[0].layer_norm.eps, tuple(c.conv_kernel), tuple(c.conv_stride),
+                                             *[l.conv.weight for l in layers], *[l.conv.bias for l in layers],
+                                             *[l.layer_norm.weight for l in layers], *[l.layer_norm.bias for l in layers])
+    raise NotImplementedError("Wav2Vec2 feature encoder: feat_extract_norm=%r with conv_bias=%r is not on the kernel path"
+                              % (c.feat_extract_norm, c.conv_bias))
 
 
 # ------------------------------------------------------------------------------------------------ patch embedding

@@ -147,3 +147,40 @@ def test_roberta_embeddings_and_feature_projection_vs_hf_modules():
     assert rel(ours2, ref2) < 2e-2 and rel(feats.grad, dfe) < 2e-2
     for k, p in w2v.feature_projection.named_parameters():
         assert rel(p.grad, want2[k]) < 2e-2, k
+
+
+@pytest.mark.parametrize("B,L", [(2, 16000), (3, 48000), (1, 4000)])
+def test_conv_feature_encoder_layer_norm_family_matches_hf(B, L):
+    """wav2vec2-large family (feat_extract_norm="layer", conv bias — the checkpoints the reference names,
+    models/tav.py:257,455) on the kernel path vs the HF module in fp32: output and every parameter gradient
+    (conv weights and biases, LayerNorm weights and biases of all 7 layers).  Same tolerance as the group-norm family."""
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+
+    from multi_modal_emotion_b200 import frontends, synthetic as syn
+
+    torch.manual_seed(0)
+    cfg = Wav2Vec2Config(num_hidden_layers=1, feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True,
+                         hidden_size=1024, num_attention_heads=16, intermediate_size=4096)
+    m = Wav2Vec2Model(cfg).cuda().eval()
+    m.load_state_dict({k: v.cuda() for k, v in syn.synth_state_dict(m, seed=10).items()})
+    g = torch.Generator().manual_seed(4)
+    wav = torch.randn(B, L, generator=g).cuda()
+    ref = m.feature_extractor(wav).transpose(1, 2)            # [B, T, C]
+    probe = torch.randn(ref.shape, generator=g).cuda()
+    (ref * probe).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in m.feature_extractor.named_parameters()}
+    assert len(ref_grads) == 28
+    m.zero_grad()
+    out = frontends.feature_extractor_cl(m, wav)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    e = rel(out, ref)
+    (out * probe).sum().backward()
+    worst = ("", 0.0)
+    for k, p in m.feature_extractor.named_parameters():
+        assert p.grad is not None, k
+        ek = rel(p.grad, ref_grads[k])
+        if ek > worst[1]:
+            worst = (k, ek)
+    print("layer-norm conv family B=%d L=%d: out rel-L2 %.2e, worst parameter gradient %.2e (%s)" % (B, L, e, worst[1], worst[0]))
+    assert e < 2e-2
+    assert worst[1] < 3e-2, worst

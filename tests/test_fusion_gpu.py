@@ -135,8 +135,9 @@ def test_encoder_api_errors():
     with pytest.raises(NotImplementedError):
         enc(torch.zeros(1, 8, 768, device="cuda"), output_attentions=True)
     te = TransformerEncoder(768, num_layers=1, dropout=0.2).cuda().train()
-    with pytest.raises(NotImplementedError):
-        te(torch.zeros(1, 8, 768, device="cuda"))
+    with pytest.raises(NotImplementedError):        # only key-padding masks [B,1,1,S] are supported
+        te(torch.zeros(1, 8, 768, device="cuda"), attention_mask=torch.zeros(1, 1, 8, 8, device="cuda"))
+    assert torch.isfinite(te(torch.randn(1, 8, 768, device="cuda"))).all()   # training-mode dropout is implemented
 
 
 @pytest.mark.parametrize("family", ["fusion", "roberta"])
