@@ -179,6 +179,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # one rank per GPU, each on its own slice of the host cores: the ranks' Python threads (graph launches, the
+        # per-step loss read-back) otherwise share one affinity mask and migrate across each other
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
         # Optional (TAVK_COMM_SMS=n): give NCCL a fixed CTA budget and keep as many SMs out of the persistent GEMM's grid
         # (tavk_reserve_sms).  Off by default: measured at 2 GPUs it costs more than it hides (649 vs 676 samples/s, n=8).
         comm_sms = int(os.environ.get("TAVK_COMM_SMS", "0"))

@@ -1,0 +1,105 @@
+"""Two NCCL ranks of the REAL model (tiny_base encoders, 12 fusion layers, weighted CE) must reproduce the single-process
+step on the concatenated batch: same global loss, same gradients after the bucketed all-reduce — first step
+(flat buffers not built yet: one whole-buffer reduce) and second step (gradient sink + bucketed all-reduces launched
+during backward from the branch streams).  Needs two GPUs: skipped otherwise (run with gpurun --gpus 2).
+
+Tolerance: the ranks sum the same per-sample gradients in a different order and with different atomics interleaving:
+loss 1e-4 absolute, whole-model flat gradient 2e-3 relative-L2, every tensor 2e-2."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(dev):
+    from multi_modal_emotion_b200 import synthetic as syn, tav
+    from multi_modal_emotion_b200.losses import NewCrossEntropyLoss
+
+    tav.set_encoder_variant("tiny_base")
+    torch.manual_seed(0)
+    model = tav.TAVForMAE({"output_dim": 7, "dropout": 0.0, "learn_PosEmbeddings": True, "num_layers": 12})
+    pre = tav.PreFormer()
+    pre.load_state_dict(syn.synth_state_dict(pre, seed=1))
+    model.load_state_dict(syn.synth_state_dict(model, seed=2))
+    crit = NewCrossEntropyLoss(class_weights=torch.tensor(syn.MELD_CLASS_WEIGHTS), epoch_switch=2)
+    return model.to(dev).train(), pre.to(dev).train(), crit
+
+
+def _named_grads(model, pre):
+    out = {}
+    for tag, m in (("TAVForMAE", model), ("PreFormer", pre)):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out["%s/%s" % (tag, k)] = p.grad.detach().clone()
+    return out
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    from multi_modal_emotion_b200 import dp, synthetic as syn
+    from multi_modal_emotion_b200.optim import FusedAdamW
+    from multi_modal_emotion_b200.tav_train import get_statistics
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    inputs, labels = syn.make_batch("C2", seed=99, B=2 * world)          # the GLOBAL batch; labels 0,3,6,2 -> mixed weights
+    shard = slice(2 * rank, 2 * rank + 2)
+    my_in = [{k: v[shard] for k, v in d.items()} for d in inputs]
+    model, pre, crit = _build(dev)
+    params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
+    opt = FusedAdamW(params, lr=0.0, weight_decay=0.0)                   # lr = 0: the parameters never move
+    runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=8)
+    seen = []
+    real_step = opt.step
+
+    def spy(*a, **kw):                                                   # the reduced gradient, right before the update
+        opt.materialize()
+        seen.append(_named_grads(model, pre))
+        return real_step(*a, **kw)
+
+    opt.step = spy
+    losses = [runner._eager_step(my_in, labels[shard], 1, "val").item() for _ in range(2)]
+    assert runner.buckets is not None and runner.buckets.launched >= 2      # step 2 went through the bucketed path
+    if rank == 0:
+        model1, pre1, crit1 = _build(dev)                                # single process, whole batch
+        loss1 = get_statistics(inputs, labels, model1, pre1, crit1, None, check="val", epoch=1)
+        loss1.backward()
+        torch.save({"losses": losses, "loss1": loss1.item(), "ref": {k: v.cpu() for k, v in _named_grads(model1, pre1).items()},
+                    "steps": [{k: v.cpu() for k, v in s.items()} for s in seen]}, tmp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_nccl_ranks_reproduce_the_single_process_step(tmp_path):
+    import torch.multiprocessing as mp
+
+    tmp = str(tmp_path / "dp2.pt")
+    mp.spawn(_worker, args=(2, _free_port(), tmp), nprocs=2, join=True)
+    r = torch.load(tmp)
+    print("global loss: 2 ranks %s vs single process %.6f" % (["%.6f" % v for v in r["losses"]], r["loss1"]))
+    for v in r["losses"]:
+        assert abs(v - r["loss1"]) < 1e-4
+    for i, got in enumerate(r["steps"]):
+        assert set(got) == set(r["ref"])
+        num = sum((got[k] - g).norm().item() ** 2 for k, g in r["ref"].items())
+        den = sum(g.norm().item() ** 2 for g in r["ref"].values())
+        gmax = max(g.norm().item() for g in r["ref"].values())
+        worst = max(((got[k] - g).norm().item() / g.norm().item(), k) for k, g in r["ref"].items() if g.norm().item() > 1e-6 * gmax)
+        print("step %d: whole-model flat gradient rel-L2 %.2e; worst tensor %.2e (%s)" % (i + 1, (num / den) ** 0.5, worst[0], worst[1]))
+        assert (num / den) ** 0.5 < 2e-3
+        assert worst[0] < 2e-2, worst

@@ -191,7 +191,9 @@ def test_gradient_sink_matches_autograd_accumulation(family):
         fwd_bwd()
     finally:
         engine.grad_written_hook = None
-    assert {id(p) for p in seen} == {id(p) for k, p in params.items() if k in ref}
+    layer_ids = {id(p) for p in params.values()}
+    # (the RoBERTa embedding tables report through the same hook since their backward became a row scatter into .grad)
+    assert {id(p) for p in seen if id(p) in layer_ids} == {id(p) for k, p in params.items() if k in ref}
     for k, r in ref.items():
         got = params[k].grad - 1.0
         assert rel(got, r) < 2e-4, (k, rel(got, r))

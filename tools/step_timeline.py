@@ -18,6 +18,12 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     cfg = sys.argv[2] if len(sys.argv) > 2 else "C2"
     out_path = sys.argv[3] if len(sys.argv) > 3 else None
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:      # torchrun: one rank per GPU; rank 0 reports its own timeline incl. every ncclAllReduce bucket
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     C = syn.CONFIGS[cfg]["C"]
     tav.set_encoder_variant("baseline")
     torch.manual_seed(0)
@@ -29,7 +35,7 @@ def main():
     crit = NewCrossEntropyLoss(torch.tensor(syn.MELD_CLASS_WEIGHTS if C == 7 else [0.5, 0.5]), epoch_switch=2)
     params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
     runner = dp.DataParallelTAV(model, pre, crit, FusedAdamW(params, lr=1e-5, weight_decay=1e-4), clip=1.0, use_cuda_graph=True)
-    inputs, labels = syn.make_batch(cfg, seed=1234, B=B)
+    inputs, labels = syn.make_batch(cfg, seed=1234 + rank, B=B)
     inputs = [{k: v.cuda() for k, v in d.items()} for d in inputs]
     labels = labels.cuda()
     runner.train_step(inputs, labels, 1, "train")
@@ -72,10 +78,29 @@ def main():
                "other tavk" if not (n.startswith("at::") or "cutlass" in n or "cudnn" in n or "Memcpy" in n or "Memset" in n) else "non-tavk (ATen/memcpy/library)")
         fam[key] += v
     lines.append("families (share of sum of durations): " + ", ".join("%s %.1f%%" % (k, 100 * v / sum(busy.values())) for k, v in sorted(fam.items(), key=lambda t: -t[1])))
+    if world > 1:
+        # every collective kernel of the step: when it ran relative to the step and to the last compute kernel of backward
+        t0 = ks[0][0]
+        nccl = [(s, e, n) for s, e, n in ks if "nccl" in n.lower()]
+        comp_before_adam = [e for s, e, n in ks if "nccl" not in n.lower() and "adamw" not in n and "sqnorm" not in n and "adamw_prep" not in n]
+        adam = [s for s, e, n in ks if "sqnorm" in n or "adamw_kernel" in n]
+        last_bwd = max(x for x in comp_before_adam if not adam or x <= adam[0]) if comp_before_adam else t0
+        lines.append("# %d ranks: %d collective kernels on rank 0; last backward compute kernel ends at %.1f us, clip+AdamW starts at %.1f us"
+                     % (world, len(nccl), last_bwd - t0, (adam[0] - t0) if adam else -1.0))
+        lines.append("%10s %10s %10s  %s" % ("start_us", "dur_us", "end_us", "collective (exposed = past the last backward kernel)"))
+        for s, e, n in nccl:
+            lines.append("%10.1f %10.1f %10.1f  %s%s" % (s - t0, e - s, e - t0, n[:60], "   EXPOSED %.1f us" % (e - last_bwd) if e > last_bwd else ""))
+        lines.append("# sum of collective kernel time %.1f us; exposed tail (last collective end - last backward end) %.1f us" % (
+            sum(e - s for s, e, n in nccl), max([e for s, e, n in nccl] + [last_bwd]) - last_bwd))
     text = "\n".join(lines)
-    print(text)
-    if out_path:
-        open(out_path, "w").write(text + "\n")
+    if rank == 0:
+        print(text)
+        if out_path:
+            open(out_path, "w").write(text + "\n")
+    if world > 1:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)     # captured graphs hold the communicator (see bench.py)
 
 
 if __name__ == "__main__":
