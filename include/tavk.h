@@ -109,6 +109,12 @@ typedef struct tavk_gemm_args {
     /* Per-call SM budget of the persistent grid (0 = every SM).  A data-parallel host passes tavk_sm_count() - n to keep
      * n SMs free for the NCCL all-reduce kernels that run concurrently with backward; there is no process-wide state. */
     int32_t max_ctas;
+    /* Optional dynamic tile scheduler: int32[2] of caller-owned device memory, zero before the first use (the kernel
+     * leaves it zero again when it finishes, so consecutive launches on one stream may share it; launches that can run
+     * CONCURRENTLY need one each).  NULL = static round-robin tiles.  With it, persistent CTAs claim output tiles from a
+     * counter: a CTA whose SM is still held by another stream's kernel or an NCCL collective claims fewer tiles
+     * instead of holding the whole grid back. */
+    void* sched_workspace;
 } tavk_gemm_args;
 int tavk_gemm_bf16(const tavk_gemm_args* args, void* stream);
 

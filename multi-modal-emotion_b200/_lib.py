@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
         ("b_box_k_shift", C.c_int32), ("out_g_row", C.c_int32), ("out_g_col", C.c_int32),
         ("a_rows", C.c_int64), ("a_cols", C.c_int64), ("b_rows", C.c_int64), ("b_cols", C.c_int64),
         ("max_ctas", C.c_int32),
+        ("sched_workspace", C.c_void_p),
     ]
 
 
@@ -164,6 +165,29 @@ def call(name, *args):
         _check(rc, name)
 
 
+# Dynamic tile scheduling of the persistent GEMM (tavk_gemm_args.sched_workspace): every gemm() call takes the next
+# {next tile, finished CTAs} pair of a per-device rotating pool, so any two launches fewer than _SCHED_SLOTS calls apart —
+# in particular kernels of different branch streams or graph branches that may run concurrently — never share one; a
+# captured graph node keeps the pair it was captured with (the kernel leaves it zeroed).  The pool is created by the first
+# call, which is never inside a stream capture (graphs are captured after eager warm-up steps).
+gemm_dynamic_tiles = os.environ.get("TAVK_GEMM_DYNAMIC", "1") != "0"
+_SCHED_SLOTS = 8192
+_sched_pools = {}
+
+
+def _sched_slot():
+    dev = torch.cuda.current_device()
+    pool = _sched_pools.get(dev)
+    if pool is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise TavkError("the GEMM scheduler workspace must exist before a CUDA graph is captured: run one eager step first")
+        pool = _sched_pools[dev] = [torch.zeros(2 * _SCHED_SLOTS, dtype=torch.int32, device=torch.device("cuda", dev)), 0]
+        torch.cuda.synchronize(dev)
+    i = pool[1]
+    pool[1] = (i + 1) % _SCHED_SLOTS
+    return pool[0].data_ptr() + 8 * i
+
+
 gemm_reserved_sms = 0   # HOST-side policy: SMs every gemm() call leaves free (passed per call as tavk_gemm_args.max_ctas)
 
 
@@ -210,6 +234,8 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
     if gemm_reserved_sms:
         a.max_ctas = lib().tavk_sm_count() - gemm_reserved_sms
+    if gemm_dynamic_tiles:
+        a.sched_workspace = _sched_slot()
     if record_gemms:
         gemm_log.append((M, N, K, int(a_mn), int(b_mn), epilogue, int(out.dtype == torch.bfloat16), int(bias is not None),
                          int(resid is not None), int(rowbias is not None), int(accumulate), k_splits,

@@ -35,7 +35,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (128, 256 or 512 columns)
     static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // one 32x32 fp32 transpose patch per epilogue warp
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct GemmDev {
@@ -63,6 +63,7 @@ struct GemmDev {
     int epilogue;
     int accumulate;
     float alpha;
+    int* sched;                     // dynamic tile scheduler workspace {next tile, finished CTAs} (NULL = static round robin)
     int tma_epi;                    // bf16 outputs leave through TMA stores (epilogue_loop_tma); see the host-side conditions
     int debug;                      // TAVK_GEMM_DEBUG (measurement only): 1 = drain TMEM and drop the tile, 2 = no global stores,
                                     // 3 = stores folded onto 128 rows (no DRAM write-back)
@@ -77,6 +78,33 @@ struct GemmDev {
 // The chunk's global operands (residual + row-bias, or the saved pre-activation) are software-pipelined one chunk
 // ahead (across tile boundaries too) in two register buffers, and the per-row work is branch-free (predicated loads
 // and stores only) so the 16 independent GELU polynomial chains of a chunk interleave.
+// Where a CTA's tiles come from.  Static: tile i of this CTA = blockIdx.x + i * gridDim.x.  Dynamic (GemmDev::sched != NULL):
+// the producer lane claims tiles from a global counter (atomicAdd) and publishes them, one tile ahead of the one it is
+// loading, through a 4-deep shared-memory ring that the MMA warp and the 8 epilogue warps read.  With one persistent CTA
+// per SM and a static split, a CTA that starts late — its SM was still busy with an NCCL all-reduce kernel or with another
+// stream's kernel (tav.branch_streams) — finishes late and the whole grid waits for it; with the counter it simply claims
+// fewer tiles.  A negative tile ends the sequence.
+constexpr int kSchedDepth = 4;
+struct TileSrc {
+    int* sched;
+    int* ring;
+    uint64_t* full;
+    uint64_t* empty;
+    int num_tiles, lane;
+    TAVK_DEVINL int get(int i) const {      // whole warp
+        if (sched == nullptr) {
+            const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+            return t < num_tiles ? (int)t : -1;
+        }
+        const int slot = i & (kSchedDepth - 1);
+        mbar_wait(&full[slot], (uint32_t)((i / kSchedDepth) & 1));
+        const int t = *reinterpret_cast<volatile int*>(ring + slot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        return t;
+    }
+};
+
 struct EpiItem {
     int row_base, col;      // first of this warp's 32 rows; this lane's first of 4 columns (global output coordinates)
     int rows_valid;         // how many of the 32 rows lie inside the (group's) M
@@ -264,7 +292,7 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
 
 template <int BLOCK_N, int MODE, int OUT>
 TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t stg, int lane, int quarter, int half,
-                               int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+                               const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
     constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     const int cc = lane & 7, rsub = lane >> 3;
     // per TILE (integer divisions live here, not in the per-chunk path): everything but the chunk's column
@@ -303,8 +331,10 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
     };
     // The work of this warp is the flat sequence of (tile, chunk) items; the global operands of item i+1 are
     // requested before item i is processed (one chunk ahead, across tile boundaries too).
-    int tile = blockIdx.x, ci = 0, it = 0;
-    if (tile >= num_tiles) return;
+    int i_tile = 0, ci = 0, it = 0;
+    int tile = src.get(0);
+    if (tile < 0) return;
+    int tile_nxt = src.get(1);              // one tile of lookahead (published before the current tile's loads start)
     TileInfo tcur = tile_info(tile);
     EpiItem w_cur = item(tcur, 0), w_nxt = w_cur;
     EpiOperands<MODE> op_cur, op_nxt;
@@ -313,8 +343,8 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
 #pragma unroll 1
     while (true) {
         int ntile = tile, nci = ci + 1;
-        if (nci == kPer) { nci = 0; ntile += (int)gridDim.x; }
-        const bool more = ntile < num_tiles;
+        if (nci == kPer) { nci = 0; ntile = tile_nxt; }
+        const bool more = ntile >= 0;
         if (more) {
             if (nci == 0) tcur = tile_info(ntile);
             w_nxt = item(tcur, nci);
@@ -333,6 +363,10 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         else epi_process<MODE, OUT, false>(p, w_cur, op_cur, taddr, stg, lane, rel);
         if (last) ++it;
         if (!more) break;
+        if (nci == 0) {                     // advanced to the next tile: fetch the one after it
+            ++i_tile;
+            tile_nxt = src.get(i_tile + 1);
+        }
         tile = ntile; ci = nci;
         w_cur = w_nxt;
         op_cur = op_nxt;
@@ -356,7 +390,7 @@ TAVK_DEVINL uint32_t sw64_off(int row, int chunk16) {      // byte offset of 16-
 template <int BLOCK_N, int MODE>
 TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2,
                                    const CUtensorMap* tmap_aux, uint32_t tmem_base, uint8_t* stg, uint64_t* aux_bar, int lane,
-                                   int quarter, int half, int num_tiles, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+                                   int quarter, int half, const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
     constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     constexpr bool kGelu = (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD);
     constexpr bool kAux = (MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL);
@@ -368,8 +402,10 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
         row0 = m_blk * kBlockM + quarter * 32;
         col0 = (mn - m_blk * p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32;
     };
-    int tile = blockIdx.x, ci = 0, it = 0, n_item = 0;
-    if (tile >= num_tiles) return;
+    int i_tile = 0, ci = 0, it = 0, n_item = 0;
+    int tile = src.get(0);
+    if (tile < 0) return;
+    int tile_nxt = src.get(1);
     int row0, col0;
     coords(tile, 0, row0, col0);
     uint32_t aux_phase = 0;
@@ -380,8 +416,8 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
 #pragma unroll 1
     while (true) {
         int ntile = tile, nci = ci + 1;
-        if (nci == kPer) { nci = 0; ntile += (int)gridDim.x; }
-        const bool more = ntile < num_tiles;
+        if (nci == kPer) { nci = 0; ntile = tile_nxt; }
+        const bool more = ntile >= 0;
         int nrow0 = 0, ncol0 = 0;
         if (more) coords(ntile, nci, nrow0, ncol0);
         // bias of the chunk's 32 columns: the same addresses in every lane (broadcast loads), issued before the waits
@@ -414,6 +450,7 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
         }
         if (p.debug == 1) {
             if (!more) break;
+            if (nci == 0) { ++i_tile; tile_nxt = src.get(i_tile + 1); }
             tile = ntile; ci = nci; row0 = nrow0; col0 = ncol0;
             continue;
         }
@@ -502,6 +539,7 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
         }
         ++n_item;
         if (!more) break;
+        if (nci == 0) { ++i_tile; tile_nxt = src.get(i_tile + 1); }
         tile = ntile; ci = nci; row0 = nrow0; col0 = ncol0;
     }
     if (lane == 0) tma_store_wait<0>();     // shared memory must outlive the last stores' reads; make them complete
@@ -526,7 +564,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
     uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;
     uint64_t* aux_bar = bars + 2 * Cfg::kStages + 4;          // one per epilogue warp (TMA-store epilogue, aux boxes)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4 + kNumEpiWarps);
+    uint64_t* sched_full = aux_bar + kNumEpiWarps;            // dynamic tile scheduler ring (TileSrc)
+    uint64_t* sched_empty = sched_full + kSchedDepth;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sched_empty + kSchedDepth);
+    int* sched_ring = reinterpret_cast<int*>(tmem_ptr_smem + 4);
 
     const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -543,6 +584,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
         }
         for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+        for (int i = 0; i < kSchedDepth; ++i) {
+            mbar_init(&sched_full[i], 1);
+            mbar_init(&sched_empty[i], 1 + kNumEpiWarps);       // the MMA warp and every epilogue warp read each entry
+        }
         if (p.tma_epi) {
             tma_prefetch_desc(&tmap_out);
             if (p.out2 != nullptr) tma_prefetch_desc(&tmap_out2);
@@ -557,6 +602,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
     const int num_tiles = p.groups * p.tiles_per_group;
+    const TileSrc src{p.sched, sched_ring, sched_full, sched_empty, num_tiles, lane};
     pdl_trigger();   // the next kernel on the stream may start its own prologue ...
     pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
 
@@ -565,7 +611,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            // tile i of this CTA: static round robin, or claimed from the global counter and published one tile ahead
+            auto claim = [&](int i) -> int {
+                if (p.sched == nullptr) {
+                    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+                    return t < num_tiles ? (int)t : -1;
+                }
+                const int c = atomicAdd(p.sched, 1);
+                const int t = c < num_tiles ? c : -1;
+                const int slot = i & (kSchedDepth - 1);
+                mbar_wait(&sched_empty[slot], (uint32_t)(((i / kSchedDepth) & 1) ^ 1));
+                *reinterpret_cast<volatile int*>(sched_ring + slot) = t;
+                mbar_arrive(&sched_full[slot]);
+                return t;
+            };
+            int tile = claim(0);
+            for (int i_tile = 0; tile >= 0; ++i_tile) {
+                const int tile_after = claim(i_tile + 1);
                 const int g = tile / p.tiles_per_group;
                 const int tg = tile - g * p.tiles_per_group;
                 const int split = tg % p.k_splits;
@@ -600,6 +662,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
+                tile = tile_after;
+            }
+            if (p.sched != nullptr) {
+                // last CTA to finish claiming resets the workspace for the next launch that uses it
+                __threadfence();
+                if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+                    p.sched[0] = 0;
+                    p.sched[1] = 0;
+                    __threadfence();
+                }
             }
         }
     } else if (warp_idx == 1) {
@@ -613,7 +685,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = src.get(0); tile >= 0; tile = src.get(++it)) {
             const int split = (tile % p.tiles_per_group) % p.k_splits;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -647,9 +719,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t stg = smem_u32(smem_stage) + ew * 4096;
 #define TAVK_EPI_TMA(MODE)                                                                                             \
     epilogue_loop_tma<BLOCK_N, MODE>(p, &tmap_out, &tmap_out2, &tmap_aux, tmem_base, smem_stage + ew * 4096, &aux_bar[ew], lane, \
-                                     quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
+                                     quarter, half, src, tmem_full_bar, tmem_empty_bar)
 #define TAVK_EPI(MODE, OUT) \
-    epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, num_tiles, tmem_full_bar, tmem_empty_bar)
+    epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, src, tmem_full_bar, tmem_empty_bar)
         if (p.tma_epi) {
             if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI_TMA(TAVK_EPI_GELU);
             else if (p.epilogue == TAVK_EPI_GELU_GRAD) TAVK_EPI_TMA(TAVK_EPI_GELU_GRAD);
@@ -789,6 +861,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     d.epilogue = a->epilogue; d.accumulate = a->accumulate; d.alpha = a->alpha;
     static const int dbg = getenv("TAVK_GEMM_DEBUG") ? atoi(getenv("TAVK_GEMM_DEBUG")) : 0;
     d.debug = dbg;
+    d.sched = reinterpret_cast<int*>(a->sched_workspace);
     d.groups = groups;
     d.tiles_per_group = d.num_m_blocks * d.num_n_blocks * d.k_splits;
     d.a_kstep = a->a_kstep > 0 ? a->a_kstep : kBlockK;
