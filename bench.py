@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--variant", default="baseline")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recompute", action="store_true",
+                    help="selective recompute: keep only layer inputs, re-run each layer's forward in backward (large batches)")
+    ap.add_argument("--no-fusion-128", action="store_true", help="skip the extra 128-sample fusion-block measurement")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples per CPU-baseline step (bounded sample)")
     return ap.parse_args()
 
@@ -50,9 +53,73 @@ def workload_name(cfg, B, variant):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def _unmodified_reference_run(args, steps, warmup, cores):
+    """The UNMODIFIED reference modules (PreFormer, TAVForMAE, NewCrossEntropyLoss) imported from where the reference tree
+    lies — baseline/_ref when someone dropped it there, /root/reference in the authoring container — on the same
+    synthetic weights and inputs.  Returns None when the tree is absent (the GPU box) or cannot be imported."""
+    import torch
+
+    from multi_modal_emotion_b200 import synthetic as syn
+    from oracle import ref_loader
+
+    if not ref_loader.available() or args.variant not in ("baseline", "reference", "tiny"):
+        return None
+    try:
+        ns = ref_loader.load_reference(args.variant)
+        B = args.cpu_batch
+        t0 = time.time()
+        C = syn.CONFIGS[args.cfg]["C"]
+        torch.manual_seed(0)
+        model = ns.TAVForMAE({"output_dim": C, "dropout": 0.4, "learn_PosEmbeddings": True, "num_layers": 12})
+        pre = ns.PreFormer()
+        pre.load_state_dict(syn.synth_state_dict(pre, seed=1))
+        model.load_state_dict(syn.synth_state_dict(model, seed=2))
+        inputs, labels = syn.make_batch(args.cfg, B=B)
+        w = torch.tensor(syn.MELD_CLASS_WEIGHTS if C == 7 else [0.5, 0.5])
+        crit = ns.NewCrossEntropyLoss(class_weights=w, epoch_switch=2)
+        params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+        ids, tm = inputs[0]["input_ids"], inputs[0]["attention_mask"]
+        wav, am = inputs[1]["audio_features"], inputs[1]["attention_mask"]
+        video, vm = inputs[2]["visual_embeds"], inputs[2]["attention_mask"]
+        build_s = time.time() - t0
+
+        def step():     # the body of train_model/tav_train.py:15-65 (get_statistics, backward, clip, AdamW)
+            t, pos, mask = pre(input_ids=ids, audio_features=wav, video_embeds=video, text_mask=tm, audio_mask=am,
+                               visual_mask=vm, device="cpu", train=False)
+            logits = model(input_ids=ids, text_attention_mask=tm, audio_features=wav, video_embeds=video, visual_mask=vm,
+                           hidden_states=t, pos_embed=pos, attention_mask=mask, batch_size=B, check="val")
+            loss = crit(logits, labels.long(), epoch=1)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss.item()
+
+        import contextlib
+
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints progress lines; stdout carries the JSON line
+            for _ in range(warmup):
+                step()
+            t0 = time.time()
+            for _ in range(steps):
+                step()
+            dt = (time.time() - t0) / max(steps, 1)
+    except Exception as e:  # noqa: BLE001  (an importable-but-broken drop must not take the bench down: fall back to the port)
+        sys.stderr.write("reference arm: unmodified reference at %s not usable (%s); using the oracle port\n" % (ref_loader.REF_ROOT, e))
+        return None
+    return {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "UNMODIFIED reference modules from %s: %d-sample batch of the same workload shape, %d timed step(s) after %d "
+                      "warm-up, fp32, torch %s CPU ops, %d threads (model build %.0fs not timed)" % (
+                          ref_loader.REF_ROOT, B, steps, warmup, torch.__version__, cores, build_s),
+            "ms_per_step": dt * 1e3}
+
+
 def cpu_reference_run(args, steps, warmup, quiet=False):
-    """The reference's own CPU implementation of the path, restated (oracle port; the reference is Python and
-    the reference tree does not travel to the GPU box), fp32, all host threads, on a bounded sample of the workload."""
+    """The reference's own CPU implementation of the path: the unmodified reference when its tree is present (see
+    _unmodified_reference_run), else the oracle port (the reference is Python and /root/reference does not travel to
+    the GPU box); fp32, all host threads, on a bounded sample of the workload (args.cpu_batch samples per step — the
+    reference at the bench's 16 samples needs ~45 GB of host memory for autograd and minutes per step)."""
     import torch
 
     from multi_modal_emotion_b200 import synthetic as syn, tav
@@ -60,6 +127,9 @@ def cpu_reference_run(args, steps, warmup, quiet=False):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    r = _unmodified_reference_run(args, steps, warmup, cores)
+    if r is not None:
+        return r
     tav.set_encoder_variant(args.variant)
     B = args.cpu_batch
     t0 = time.time()
@@ -95,6 +165,65 @@ def cpu_reference_run(args, steps, warmup, quiet=False):
             "sample": "%d-sample batch of the same workload shape, %d timed step(s) after %d warm-up, fp32, torch %s CPU ops, "
                       "%d threads (model build %.0fs not timed)" % (B, steps, warmup, torch.__version__, cores, build_s),
             "ms_per_step": dt * 1e3}
+
+
+def torch_gpu_baseline(args, B):
+    """Informational (SURVEY 0 / 8c "beat eager PyTorch on the same B200"): the plain-PyTorch restatement of the reference
+    (oracle/) moved to the same GPU — eager ATen / cuBLAS / SDPA kernels — in fp32 and under bf16 autocast, one
+    fwd + weighted CE + bwd + clip + AdamW step at the bench's own batch.  Not the product path, never the thing shipped."""
+    import torch
+
+    from multi_modal_emotion_b200 import synthetic as syn, tav
+    from oracle import tav_oracle as O
+
+    out = {}
+    try:
+        tav.set_encoder_variant(args.variant)
+        C = syn.CONFIGS[args.cfg]["C"]
+        model = tav.TAVForMAE({"output_dim": C, "dropout": 0.4, "learn_PosEmbeddings": True, "num_layers": 12})
+        pre = tav.PreFormer()
+        pre_sd, tav_sd = syn.synth_state_dict(pre, seed=1), syn.synth_state_dict(model, seed=2)
+        del model, pre
+        orc = O.OracleTAV(tav.encoder_configs(args.variant)).load(pre_sd, tav_sd).to("cuda")
+        params = [p for m in list(orc.pre.values()) + list(orc.tav.values()) for p in m.parameters()] + \
+            list(orc.pre_w.values()) + list(orc.tav_w.values())
+        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+        inputs, labels = syn.make_batch(args.cfg, B=B)
+        inputs = [{k: v.cuda() for k, v in d.items()} for d in inputs]
+        labels = labels.cuda().long()
+        w = torch.tensor(syn.MELD_CLASS_WEIGHTS if C == 7 else [0.5, 0.5]).cuda()
+        for name, ctx in (("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16)), ("fp32", None)):
+            def step():
+                if ctx is None:
+                    logits = orc.forward(inputs)
+                else:
+                    with ctx():
+                        logits = orc.forward(inputs)
+                loss = O.new_cross_entropy(logits.float(), labels, 1, w, 2)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 1.0)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+
+            for _ in range(3):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            n = 5
+            for _ in range(n):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[name] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
+        out["what"] = ("oracle restatement of the reference on the same GPU, eager PyTorch %s (ATen/cuBLAS/SDPA), batch %d, "
+                       "fwd + weighted CE + bwd + clip + AdamW, CUDA events, 3 warm-up + 5 timed steps" % (torch.__version__, B))
+        del orc, params, opt
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001  (informational leg: never fails the bench)
+        out["error"] = str(e)[:300]
+    return out
 
 
 def reference_main(args):
@@ -197,6 +326,12 @@ def main():
         if comm_sms > 0:
             L.reserve_sms(comm_sms)
     L.require_device()   # fails loudly when the CUDA extension / an sm_100 device is missing: no fallback
+    if args.no_fusion_128:
+        os.environ["TAVK_BENCH_NO_FUSION128"] = "1"
+    if args.recompute:
+        from multi_modal_emotion_b200 import engine
+
+        engine.recompute_layers = True
 
     peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
     try:
@@ -304,7 +439,8 @@ def main():
             "config": {"workload": workload_name(cfg, B, args.variant), "global_batch": B * world,
                        "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
                        "l2_policy": "inputs (%.0f MB/step) and saved activations exceed the 126 MB L2; no explicit flush" % (h2d / 1e6),
-                       "step": "fwd + loss + bwd + grad all-reduce + clip + AdamW"},
+                       "step": "fwd + loss + bwd + grad all-reduce + clip + AdamW",
+                       "activation_recompute": bool(args.recompute)},
             "e2e": {"value": B * world / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e,
                     "how": "train_step(host batch, next_batch=...): pinned-host H2D of every batch (copy of batch i+1 "
@@ -315,6 +451,9 @@ def main():
             "peaks": peaks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            del runner, model, pre, opt
+            torch.cuda.empty_cache()
+            line["torch_gpu"] = torch_gpu_baseline(args, B)
             r = cpu_reference_run(args, 1, 1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -443,6 +582,8 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
                 "flops": fl, "mask_regime": "R (reference PreFormer masks)"}
 
     fusion = fusion_at(B)
+    if os.environ.get("TAVK_BENCH_NO_FUSION128"):
+        return roof, fusion
     try:
         fusion["batch_128"] = fusion_at(128)
     except Exception as e:  # noqa: BLE001  (e.g. out of memory on a smaller part): the B-sized figure stands

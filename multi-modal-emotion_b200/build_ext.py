@@ -2,6 +2,8 @@
 
 nvcc cross-compiles without a GPU, so this runs in the authoring container as well as on the B200 box; the built
 ``libtavk.so`` next to this file is what travels to the GPU box."""
+import hashlib
+import json
 import os
 import shutil
 import subprocess
@@ -29,25 +31,46 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+def _digest(paths, extra=""):
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(os.path.basename(p).encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
+STAMP = os.path.join(OBJ, "build_info.json")
+last_build = None     # {"mode": "compiled" | "reused (content hash verified)", "sources_compiled": [...], "sha256": ...}
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu -> build/*.o -> libtavk.so; no-op when up to date.  Returns the library path."""
+    """Compile csrc/*.cu -> build/*.o -> libtavk.so.  Staleness is decided by CONTENT: every object records the sha256 of
+    its source + the shared headers + the compiler flags, the library records the digest of all of them, and a stored
+    object / library is reused only when its recorded digest matches what is on disk now (mtimes say nothing after a
+    checkout or an rsync).  TAVK_FORCE_BUILD=1 or force=True recompiles everything.  ``last_build`` / build/build_info.json
+    say what happened, so a driver can tell an exercised build from a reused binary.  Returns the library path."""
+    global last_build
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
+    force = force or os.environ.get("TAVK_FORCE_BUILD", "") == "1"
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "tavk.h")]
-    jobs = []
+    flags = " ".join(NVCC_FLAGS)
+    try:
+        with open(STAMP) as f:
+            stamp = json.load(f)
+    except Exception:  # noqa: BLE001
+        stamp = {}
+    recorded = stamp.get("objects", {})
+    jobs, digests, compiled = [], {}, []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s.replace(".cu", ".o"))
-        if force or _stale(obj, [src] + headers):
+        digests[s] = _digest([src] + headers, flags)
+        if force or not os.path.exists(obj) or recorded.get(s) != digests[s]:
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
+            compiled.append(s)
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -61,7 +84,9 @@ def build_library(force=False, verbose=False):
                 if verbose and out:
                     print(out, file=sys.stderr)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
+    lib_digest = hashlib.sha256("".join(digests[s] for s in SOURCES).encode()).hexdigest()
+    relink = force or bool(jobs) or not os.path.exists(LIB) or stamp.get("library") != lib_digest
+    if relink:
         rpaths = ["/usr/local/cuda/lib64"]
         try:
             import nvidia.cuda_runtime  # torch's bundled runtime, preferred at load time
@@ -73,6 +98,10 @@ def build_library(force=False, verbose=False):
         for rp in rpaths:
             link += ["-Xlinker", "-rpath", "-Xlinker", rp]
         run(link)
+    last_build = {"mode": "compiled" if relink else "reused (content hash verified)", "sources_compiled": compiled,
+                  "sha256": lib_digest, "nvcc_flags": flags}
+    with open(STAMP, "w") as f:
+        json.dump({"objects": digests, "library": lib_digest, "last": last_build}, f, indent=1)
     return LIB
 
 

@@ -440,6 +440,13 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
     return dx, dx_bf, go.results(), go.written()
 
 
+# Selective recompute (BASELINE configs[4] sweeps the per-GPU batch to 256): when set, a stack keeps only each
+# layer's fp32 INPUT (4·H bytes per token instead of ~58·H: LN outputs, packed QKV, attention output, FFN activations ...)
+# and re-runs the layer's forward inside the backward.  One extra forward per layer (+1/3 of the stack's FLOPs) buys a
+# ~12x smaller activation footprint: at 256 samples per GPU the VideoMAE stack alone would save 166 GB, against 14 GB.
+recompute_layers = False
+
+
 class EncoderStackFn(torch.autograd.Function):
     """y = layers_n(...layers_1(x)); x f32 [B,S,H]; mask2d f32 [B,S] or None; params = N_SLOTS entries per layer."""
 
@@ -450,6 +457,7 @@ class EncoderStackFn(torch.autograd.Function):
         assert H == spec.hidden and x.dtype == torch.float32
         n_layers = len(params) // N_SLOTS
         keep = any(ctx.needs_input_grad)  # inference: nothing is saved
+        recompute = keep and recompute_layers and spec.dropout == 0.0   # (dropout masks are not regenerated)
         cur = x.contiguous().view(B * S, H)
         if mask2d is not None:
             mask2d = mask2d.contiguous().float()
@@ -458,11 +466,17 @@ class EncoderStackFn(torch.autograd.Function):
         for li in range(n_layers):
             p = params[li * N_SLOTS:(li + 1) * N_SLOTS]
             sh = shadows[li].refresh(p, spec)
-            cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep, li)
-            saved.append(sv)
+            if recompute:
+                x_in = cur
+                cur, cur_bf, _ = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, False, li)
+                saved.append(x_in)
+            else:
+                cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep, li)
+                saved.append(sv)
         if spec.dropout > 0.0 and not spec.pre_ln:
             _dropout_counter[x.device].add_(1)   # device-side: the next call (or graph replay) draws fresh masks
         ctx.spec, ctx.shadows, ctx.saved, ctx.mask2d, ctx.params, ctx.dims = spec, shadows, saved, mask2d, params, (B, S, H)
+        ctx.recompute = recompute
         return cur.view(B, S, H)
 
     @staticmethod
@@ -486,7 +500,10 @@ class EncoderStackFn(torch.autograd.Function):
                 cs_t = _sink(below_b2)
                 if cs_t is None:
                     cs_t = cs_tmp = torch.zeros(below_b2.shape, dtype=torch.float32, device=dy.device)
-            dy, dy_bf, g, written = _layer_bwd(spec, p, ctx.shadows[li], ctx.saved[li], dy, dy_bf, B, S, ctx.mask2d,
+            sv = ctx.saved[li]
+            if ctx.recompute:      # sv is the layer's input: rebuild what the backward needs
+                _, _, sv = _layer_fwd(spec, p, ctx.shadows[li], sv, None, B, S, ctx.mask2d, True, li)
+            dy, dy_bf, g, written = _layer_bwd(spec, p, ctx.shadows[li], sv, dy, dy_bf, B, S, ctx.mask2d,
                                                need_dx_bf=(li > 0 and spec.pre_ln), b2_done=b2_done, dx_colsum=cs_t)
             ctx.saved[li] = None  # free activations as we go
             for k, gk in enumerate(g):

@@ -10,11 +10,21 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TAV_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _is_ref(root):
+    return bool(root) and os.path.isfile(os.path.join(root, "models", "tav.py")) and os.path.isfile(os.path.join(root, "utils", "TAVFormer.py"))
+
+
+# where the unmodified reference may lie: an explicit override, the authoring container's read-only checkout, or
+# baseline/_ref — the git-ignored place the driver (or an operator) may drop the reference tree for the bench's reference arm
+REF_ROOT = next((r for r in (os.environ.get("TAV_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref"))
+                 if _is_ref(r)), "/root/reference")
 
 
 def available():
-    return os.path.isdir(os.path.join(REF_ROOT, "models")) and os.path.isfile(os.path.join(REF_ROOT, "utils", "TAVFormer.py"))
+    return _is_ref(REF_ROOT)
 
 
 def _stub(name, attrs=()):

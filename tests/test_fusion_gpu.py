@@ -250,3 +250,44 @@ def test_custom_encoder_training_mode_dropout_vs_oracle_with_the_same_masks():
     finally:
         engine.debug_dropout_masks = None
     assert not torch.equal(again[0], masks[0])
+
+
+@pytest.mark.parametrize("family", ["fusion", "custom"])
+def test_selective_recompute_gives_the_same_gradients(family):
+    """engine.recompute_layers keeps only each layer's input and re-runs its forward inside backward (BASELINE configs[4]:
+    per-GPU batches up to 256): identical outputs, gradients equal up to the order of the atomically accumulated sums."""
+    from transformers import VideoMAEConfig
+
+    from multi_modal_emotion_b200 import engine, synthetic as syn
+    from multi_modal_emotion_b200.tavformer import TransformerEncoder, VideoMAEEncoder
+
+    g = torch.Generator().manual_seed(13)
+    B, S = 2, 200
+    x = torch.randn(B, S, 768, generator=g)
+    if family == "fusion":
+        enc = VideoMAEEncoder(VideoMAEConfig(), 3)
+        mask = syn.reference_masks(B, 40, 60, 100, torch.tensor([40, 11]), torch.tensor([60, 30])).cuda()
+    else:
+        enc = TransformerEncoder(768, num_layers=2, dropout=0.0)
+        mask = None
+    enc.load_state_dict(syn.synth_state_dict(enc, seed=14))
+    enc = enc.cuda()
+    probe = torch.randn(B, S, 768, generator=g).cuda()
+    out = {}
+    for flag in (False, True):
+        engine.recompute_layers = flag
+        try:
+            enc.zero_grad(set_to_none=True)
+            xg = x.cuda().requires_grad_(True)
+            y = enc(xg, mask)
+            (y * probe).sum().backward()
+            out[flag] = (y.detach().clone(), xg.grad.clone(), {k: p.grad.clone() for k, p in enc.named_parameters() if p.grad is not None})
+        finally:
+            engine.recompute_layers = False
+    assert torch.equal(out[True][0], out[False][0])
+    assert rel(out[True][1], out[False][1]) < 1e-5
+    assert set(out[True][2]) == set(out[False][2])
+    gmax = max(v.norm().item() for v in out[False][2].values())
+    for k, v in out[False][2].items():
+        if v.norm().item() > 1e-6 * gmax:
+            assert rel(out[True][2][k], v) < 1e-4, k
