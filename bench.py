@@ -55,7 +55,7 @@ def workload_name(cfg, B, variant):
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def _unmodified_reference_run(args, steps, warmup, cores):
     """The UNMODIFIED reference modules (PreFormer, TAVForMAE, NewCrossEntropyLoss) imported from where the reference tree
-    lies — baseline/_ref when someone dropped it there, /root/reference in the authoring container — on the same
+    lies — baseline/_ref when someone dropped it there, the read-only checkout of the authoring container — on the same
     synthetic weights and inputs.  Returns None when the tree is absent (the GPU box) or cannot be imported."""
     import torch
 
@@ -117,7 +117,7 @@ def _unmodified_reference_run(args, steps, warmup, cores):
 
 def cpu_reference_run(args, steps, warmup, quiet=False):
     """The reference's own CPU implementation of the path: the unmodified reference when its tree is present (see
-    _unmodified_reference_run), else the oracle port (the reference is Python and /root/reference does not travel to
+    _unmodified_reference_run), else the oracle port (the reference is Python and its checkout does not travel to
     the GPU box); fp32, all host threads, on a bounded sample of the workload (args.cpu_batch samples per step — the
     reference at the bench's 16 samples needs ~45 GB of host memory for autograd and minutes per step)."""
     import torch
