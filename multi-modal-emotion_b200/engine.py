@@ -223,8 +223,10 @@ def _drop_bwd(dy, keep, p, resid=None):
     return dx
 
 
-def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0):
-    """x: f32 [M,H].  Returns (y_f32, y_bf16 or None, saved)."""
+def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0, same_as_training=False):
+    """x: f32 [M,H].  Returns (y_f32, y_bf16 or None, saved).  ``same_as_training``: use the training forward's epilogues
+    even though nothing is kept (selective recompute: the first pass and the pass re-run in backward must agree bit for bit)."""
+    train_epi = keep or same_as_training
     H, I = spec.hidden, spec.inter
     M = B * S
     dev = x.device
@@ -248,7 +250,7 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0):
         # `pre` receives gelu'(pre-activation) when a backward will follow (EPI_GELU_GRAD): the backward's dgrad GEMM then
         # only multiplies by it (EPI_MUL) instead of evaluating the GELU derivative in its (issue-bound) epilogue
         pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
-        L.gemm(h2, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
+        L.gemm(h2, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if train_epi else L.EPI_GELU)
         y = _f32((M, H), dev)
         L.gemm(act, sh.w2, y, M=M, N=H, K=I, bias=d["b2"], resid=x1)
         if keep:
@@ -280,7 +282,7 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0):
         yd, m2 = _drop_fwd(y_f32, pd, li, 1, spec)
         ff_in = L.cast_bf16(yd)
     pre, act = _bf16((M, I), dev), _bf16((M, I), dev)
-    L.gemm(ff_in, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if keep else L.EPI_GELU)
+    L.gemm(ff_in, sh.w1, pre, M=M, N=I, K=H, bias=d["b1"], out2=act, epilogue=L.EPI_GELU_GRAD if train_epi else L.EPI_GELU)
     f = _f32((M, H), dev)
     L.gemm(act, sh.w2, f, M=M, N=H, K=I, bias=d["b2"], resid=y_f32)
     if pd > 0.0:
@@ -468,7 +470,7 @@ class EncoderStackFn(torch.autograd.Function):
             sh = shadows[li].refresh(p, spec)
             if recompute:
                 x_in = cur
-                cur, cur_bf, _ = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, False, li)
+                cur, cur_bf, _ = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, False, li, same_as_training=True)
                 saved.append(x_in)
             else:
                 cur, cur_bf, sv = _layer_fwd(spec, p, sh, cur, cur_bf, B, S, mask2d, keep, li)
