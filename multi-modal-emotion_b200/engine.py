@@ -12,6 +12,7 @@ Numerics: the residual stream, LayerNorm statistics, biases, the rank-1 term and
 GEMM / attention operands are bf16 with fp32 accumulation (tcgen05 / mma.sync).  Weights stay fp32 ``nn.Parameter``s
 (state_dict compatible); bf16 operand copies ("shadows", QKV packed to [3H,H]) are cached per layer and refreshed when
 a parameter's version counter changes or ``invalidate_shadows()`` is called by the fused optimiser."""
+import os
 from dataclasses import dataclass
 
 import torch
@@ -546,8 +547,18 @@ class _LayerNormFn(torch.autograd.Function):
         return dx.view(ctx.shp), dw, db, None
 
 
+# The small operators below are the torch custom ops of ops.py (torch.ops.tavk.*: schema + fake implementation +
+# register_autograd over the same C-ABI entry points) — the modules reach the kernels through that layer, as the boundary
+# asks.  TAVK_ENGINE_DIRECT=1 keeps the in-file autograd Functions instead (identical kernels).
+_VIA_OPS = os.environ.get("TAVK_ENGINE_DIRECT", "0") != "1"
+
+
 def layer_norm(x, w, b, eps=1e-5):
     """nn.LayerNorm over the last dim through tavk_layernorm_{fwd,bwd} (reference models/tav.py:486,488-490)."""
+    if _VIA_OPS:
+        from . import ops
+
+        return ops.layer_norm(x, w, b, eps)
     return _LayerNormFn.apply(x, w, b, eps)
 
 
@@ -577,6 +588,10 @@ def mean_pool(x, lengths=None):
     """torch.mean(x, dim=1) (reference models/tav.py:478,481,488; unmasked — SURVEY Q3).  ``lengths`` (int [B]) selects the
     masked mean over the first lengths[b] tokens of each sample instead (the boundary's optional argument; the
     reference itself never passes one)."""
+    if _VIA_OPS and lengths is None:
+        from . import ops
+
+        return ops.mean_pool(x)
     return _MeanPoolFn.apply(x, lengths)
 
 
@@ -606,6 +621,10 @@ class _EmbedAddFn(torch.autograd.Function):
 
 def embed_add(x, idx, table):
     """x + table[idx] (reference models/tav.py:474)."""
+    if _VIA_OPS:
+        from . import ops  # noqa: F401  (registers torch.ops.tavk)
+
+        return torch.ops.tavk.embed_add(x, idx, table)
     return _EmbedAddFn.apply(x, idx, table)
 
 
@@ -706,6 +725,10 @@ class _SmallLinearFn(torch.autograd.Function):
 
 def small_linear(x, w, b=None):
     """fp32 linear for launch-bound shapes: the classifier head Linear(3072, C) (reference models/tav.py:499)."""
+    if _VIA_OPS:
+        from . import ops
+
+        return ops.small_linear(x, w, b)
     return _SmallLinearFn.apply(x, w, b)
 
 
@@ -744,6 +767,10 @@ class _LinearBf16Fn(torch.autograd.Function):
 
 
 def linear_bf16(x, w, b=None):
+    if _VIA_OPS:
+        from . import ops  # noqa: F401
+
+        return torch.ops.tavk.linear(x, w, b)
     return _LinearBf16Fn.apply(x, w, b)
 
 
@@ -781,7 +808,14 @@ def dropout(x, p, seed=None):
     c = _dropout_counter.get(x.device)
     if c is None:
         c = _dropout_counter[x.device] = torch.zeros(1, dtype=torch.int64, device=x.device)
-    return _DropoutFn.apply(x, p, (torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF, c)
+    seed = (torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+    if _VIA_OPS:
+        from . import ops  # noqa: F401
+
+        y, _ = torch.ops.tavk.dropout(x, float(p), seed, c)
+        c.add_(1)  # device-side: also advances on every CUDA-graph replay
+        return y
+    return _DropoutFn.apply(x, p, seed, c)
 
 
 def reset_dropout_counter():

@@ -14,6 +14,13 @@ in place — something a per-op graph cannot express.
   tavk::softmax_ce(logits, target, weight)       (sum_i w_yi l_i, sum_i w_yi)     (utils/global_functions.py:63-83)
   tavk::attention(qkv, heads, key_bias)          softmax(QK^T/sqrt(d) + bias) V from a packed [B,S,3H] bf16 tensor
                                                  (utils/TAVFormer.py:357-387, :60-86), head_dim 64
+  tavk::linear(x, w, b)                          F.linear on the tcgen05 GEMM: bf16 operands, fp32 accumulate/out; backward
+                                                 = the dgrad / wgrad forms of the same entry point (utils/TAVFormer.py:348-350,
+                                                 :404,:422,:434; models/tav.py:363,478)
+  tavk::embed_add(x, idx, table)                 x + table[idx]                   (models/tav.py:474)
+  tavk::dropout(x, p, seed, counter)             nn.Dropout(p) training mode, counter-based generator (models/tav.py:497-498)
+  tavk::adamw_step(p, m, v, g, ...)              clip_grad_norm_ + AdamW.step over flat buffers, device-resident clock
+                                                 (train_model/tav_train.py:61-63,148-149); mutates its arguments
 
 There is no CPU implementation: calling one with CPU tensors raises (the fake implementations only propagate shapes)."""
 from typing import Optional, Tuple
@@ -285,5 +292,180 @@ def _attn_backward(ctx, d_o, _dlse):
 
 attention.register_autograd(_attn_backward, setup_context=_attn_setup)
 
+
+# ------------------------------------------------------------------------------------------------ linear (tcgen05 GEMM)
+@torch.library.custom_op("tavk::linear", mutates_args=())
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    _need_cuda(x, w, b)
+    K, N = x.shape[-1], w.shape[0]
+    x2 = x.contiguous().view(-1, K)
+    M = x2.shape[0]
+    x_bf = x2 if x2.dtype == _BF16 else L.cast_bf16(x2.float())
+    w_bf = w if w.dtype == _BF16 else L.cast_bf16(w.detach().float())
+    y = torch.empty((M, N), dtype=_F32, device=x.device)
+    L.gemm(x_bf, w_bf.contiguous(), y, M=M, N=N, K=K, bias=None if b is None else b.float().contiguous())
+    return y.view(*x.shape[:-1], N)
+
+
+@linear.register_fake
+def _(x, w, b):
+    return x.new_empty((*x.shape[:-1], w.shape[0]), dtype=_F32)
+
+
+@torch.library.custom_op("tavk::linear_bwd", mutates_args=())
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, has_bias: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(dx, dw, db): dgrad (A = dY K-major, B = W MN-major), wgrad (both MN-major, split-K, accumulate) and the bias column sum."""
+    _need_cuda(dy, x, w)
+    K, N = x.shape[-1], w.shape[0]
+    x2 = x.contiguous().view(-1, K)
+    M = x2.shape[0]
+    x_bf = x2 if x2.dtype == _BF16 else L.cast_bf16(x2.float())
+    w_bf = (w if w.dtype == _BF16 else L.cast_bf16(w.detach().float())).contiguous()
+    dy2 = dy.contiguous().view(M, N).float()
+    dy_bf = L.cast_bf16(dy2)
+    dx = torch.empty((M, K), dtype=_F32, device=x.device)
+    L.gemm(dy_bf, w_bf, dx, M=M, N=K, K=N, b_mn=True)
+    dw = torch.zeros((N, K), dtype=_F32, device=x.device)
+    tiles = ((N + 127) // 128) * ((K + 255) // 256)
+    L.gemm(dy_bf, x_bf, dw, M=N, N=K, K=M, a_mn=True, b_mn=True, accumulate=True,
+           k_splits=max(1, min(148 // max(tiles, 1), (M + 511) // 512)))
+    db = torch.zeros((N if has_bias else 0,), dtype=_F32, device=x.device)
+    if has_bias:
+        L.colsum(dy2, db, M=M, N=N)
+    return dx.view(x.shape), dw, db
+
+
+@linear_bwd.register_fake
+def _(dy, x, w, has_bias):
+    return x.new_empty(x.shape, dtype=_F32), w.new_empty(w.shape, dtype=_F32), w.new_empty((w.shape[0] if has_bias else 0,), dtype=_F32)
+
+
+def _linear_setup(ctx, inputs, output):
+    x, w, b = inputs
+    ctx.save_for_backward(x, w)
+    ctx.has_b = b is not None
+
+
+def _linear_backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    dx, dw, db = linear_bwd(dy, x, w, ctx.has_b)
+    return dx.to(x.dtype), dw.to(w.dtype), (db if ctx.has_b else None)
+
+
+linear.register_autograd(_linear_backward, setup_context=_linear_setup)
+
+
+# ------------------------------------------------------------------------------------------------ embed_add
+@torch.library.custom_op("tavk::embed_add", mutates_args=())
+def embed_add(x: torch.Tensor, idx: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, idx, table)
+    B, S, H = x.shape
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    L.call("tavk_embed_add_fwd", x.data_ptr(), idx.contiguous().long().data_ptr(), table.float().contiguous().data_ptr(),
+           y.data_ptr(), B * S, H, table.shape[0])
+    return y
+
+
+@embed_add.register_fake
+def _(x, idx, table):
+    return x.new_empty(x.shape, dtype=_F32)
+
+
+@torch.library.custom_op("tavk::embed_add_bwd", mutates_args=())
+def embed_add_bwd(dy: torch.Tensor, idx: torch.Tensor, n_embed: int) -> torch.Tensor:
+    _need_cuda(dy, idx)
+    B, S, H = dy.shape
+    dy = dy.contiguous().float()
+    dt = torch.zeros((n_embed, H), dtype=_F32, device=dy.device)
+    L.call("tavk_embed_add_bwd", dy.data_ptr(), idx.contiguous().long().data_ptr(), dt.data_ptr(), B * S, H, n_embed)
+    return dt
+
+
+@embed_add_bwd.register_fake
+def _(dy, idx, n_embed):
+    return dy.new_empty((n_embed, dy.shape[-1]), dtype=_F32)
+
+
+def _embed_setup(ctx, inputs, output):
+    _, idx, table = inputs
+    ctx.save_for_backward(idx)
+    ctx.n = table.shape[0]
+
+
+def _embed_backward(ctx, dy):
+    (idx,) = ctx.saved_tensors
+    return dy, None, embed_add_bwd(dy, idx, ctx.n)
+
+
+embed_add.register_autograd(_embed_backward, setup_context=_embed_setup)
+
+
+# ------------------------------------------------------------------------------------------------ dropout
+@torch.library.custom_op("tavk::dropout", mutates_args=())
+def dropout(x: torch.Tensor, p: float, seed: int, counter: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(y, keep mask uint8).  ``counter``: device int64 scalar added to the stream position, so a captured CUDA graph draws
+    a fresh mask per replay when the caller increments it (engine.dropout does)."""
+    _need_cuda(x, counter)
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    keep = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    L.call("tavk_dropout", x.data_ptr(), y.data_ptr(), keep.data_ptr(), x.numel(), float(p), int(seed) & 0x7FFFFFFFFFFFFFFF, 0,
+           counter.data_ptr())
+    return y, keep
+
+
+@dropout.register_fake
+def _(x, p, seed, counter):
+    return x.new_empty(x.shape, dtype=_F32), x.new_empty(x.shape, dtype=torch.uint8)
+
+
+@torch.library.custom_op("tavk::dropout_bwd", mutates_args=())
+def dropout_bwd(dy: torch.Tensor, keep: torch.Tensor, p: float) -> torch.Tensor:
+    _need_cuda(dy, keep)
+    dy = dy.contiguous().float()
+    dx = torch.empty_like(dy)
+    L.call("tavk_dropout_bwd", dy.data_ptr(), keep.data_ptr(), dx.data_ptr(), dy.numel(), float(p))
+    return dx
+
+
+@dropout_bwd.register_fake
+def _(dy, keep, p):
+    return dy.new_empty(dy.shape, dtype=_F32)
+
+
+def _drop_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.p = inputs[1]
+
+
+def _drop_backward(ctx, dy, _dkeep):
+    (keep,) = ctx.saved_tensors
+    return dropout_bwd(dy, keep, ctx.p), None, None, None
+
+
+dropout.register_autograd(_drop_backward, setup_context=_drop_setup)
+
+
+# ------------------------------------------------------------------------------------------------ optimiser step
+@torch.library.custom_op("tavk::adamw_step", mutates_args=("p", "m", "v", "g", "p_bf16", "step", "hyper", "sqnorm"))
+def adamw_step(p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, g: torch.Tensor, p_bf16: torch.Tensor, step: torch.Tensor,
+               hyper: torch.Tensor, sqnorm: torch.Tensor, beta1: float, beta2: float, eps: float, weight_decay: float,
+               max_norm: float, grad_prescale: float) -> None:
+    """clip_grad_norm_(max_norm) + AdamW over flat fp32 buffers, in place; writes the bf16 mirror of the parameters and zeroes
+    the gradient.  ``step`` (int32[1]) and ``hyper`` (f32[4], hyper[0] = learning rate) are the device-resident optimiser
+    clock: the op advances them, so it is CUDA-graph safe (include/tavk.h tavk_adamw_prep / tavk_adamw_dev)."""
+    _need_cuda(p, m, v, g, p_bf16, step, hyper, sqnorm)
+    n = p.numel()
+    use_clip = max_norm > 0
+    L.call("tavk_adamw_prep", step.data_ptr(), hyper.data_ptr(), sqnorm.data_ptr() if use_clip else None, beta1, beta2)
+    if use_clip:
+        L.call("tavk_grad_sqnorm", g.data_ptr(), n, sqnorm.data_ptr())
+    L.call("tavk_adamw_dev", p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), p_bf16.data_ptr(), n, hyper.data_ptr(),
+           beta1, beta2, eps, weight_decay, sqnorm.data_ptr() if use_clip else None, max_norm if use_clip else 0.0,
+           grad_prescale, 1)
+
+
 OPS = ("layer_norm_fwd", "layer_norm_bwd", "mean_pool", "mean_pool_bwd", "small_linear", "small_linear_bwd", "softmax_ce",
-       "softmax_ce_bwd", "attention", "attention_bwd")
+       "softmax_ce_bwd", "attention", "attention_bwd", "linear", "linear_bwd", "embed_add", "embed_add_bwd", "dropout",
+       "dropout_bwd", "adamw_step")

@@ -35,6 +35,17 @@ def test_fake_tensor_shapes_forward_and_backward():
         assert o.shape == (2, 323, 768) and o.dtype == torch.bfloat16 and lse.shape == (2, 12, 323)
         o.float().sum().backward()
         assert qkv.grad.shape == qkv.shape
+        # linear (tcgen05 GEMM) -> embed_add -> dropout: shapes through forward and backward
+        xl = torch.empty(2, 149, 1024, requires_grad=True)
+        wl, bl = torch.empty(768, 1024, requires_grad=True), torch.empty(768, requires_grad=True)
+        table = torch.empty(3, 768, requires_grad=True)
+        h = torch.ops.tavk.linear(xl, wl, bl)
+        h = torch.ops.tavk.embed_add(h, torch.empty(2, 149, dtype=torch.long), table)
+        h, keep = torch.ops.tavk.dropout(h, 0.4, 123, torch.empty(1, dtype=torch.long))
+        assert h.shape == (2, 149, 768) and keep.dtype == torch.uint8
+        h.sum().backward()
+        assert xl.grad.shape == xl.shape and wl.grad.shape == wl.shape and bl.grad.shape == (768,) and table.grad.shape == (3, 768)
+        assert torch.ops.tavk.linear(xl, wl, None).shape == (2, 149, 768)
 
 
 def test_cpu_tensors_are_refused():

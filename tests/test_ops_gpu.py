@@ -80,3 +80,69 @@ def test_attention_operator_matches_torch(use_bias):
     assert rel(qkv.grad, want) < 1.5e-2
     torch.library.opcheck(torch.ops.tavk.attention, (qkv.detach().clone().requires_grad_(True), nh, bias),
                           test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_linear_embed_add_dropout_adamw_operators():
+    """tavk::linear (tcgen05 GEMM forward / dgrad / wgrad), embed_add, dropout and the fused optimiser step as torch custom
+    ops: against torch (bf16-operand tolerance for linear, fp32 for the rest) and through torch.library.opcheck."""
+    from multi_modal_emotion_b200 import _lib, ops  # noqa: F401
+
+    _lib.require_device()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 149, 1024, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(768, 1024, generator=g) * 0.03).cuda().requires_grad_(True)
+    b = (torch.randn(768, generator=g) * 0.1).cuda().requires_grad_(True)
+    table = torch.randn(3, 768, generator=g).cuda().requires_grad_(True)
+    idx = torch.randint(0, 3, (2, 149), generator=g).cuda()
+    probe = torch.randn(2, 149, 768, generator=g).cuda()
+
+    def run(lin, emb):
+        for t in (x, w, b, table):
+            t.grad = None
+        y = emb(lin(x, w, b), idx, table)
+        (y * probe).sum().backward()
+        return y.detach(), [t.grad.clone() for t in (x, w, b, table)]
+
+    ours = run(torch.ops.tavk.linear, torch.ops.tavk.embed_add)
+    ref = run(F.linear, lambda h, i, t: h + t[i])
+    assert rel(ours[0], ref[0]) < 6e-3
+    for a, r, tol in zip(ours[1], ref[1], (1e-2, 1e-2, 1e-4, 1e-4)):
+        assert rel(a, r) < tol
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    xd = torch.randn(64, 768, generator=g).cuda().requires_grad_(True)
+    y, keep = torch.ops.tavk.dropout(xd, 0.4, 1234, counter)
+    assert abs(keep.float().mean().item() - 0.6) < 2e-2
+    assert torch.equal(y, torch.where(keep.bool(), xd.detach() / 0.6, torch.zeros_like(y)))
+    y.sum().backward()
+    assert torch.equal(xd.grad, keep.float() / 0.6)
+    counter.add_(1)
+    assert not torch.equal(torch.ops.tavk.dropout(xd, 0.4, 1234, counter)[1], keep)
+    # fused optimiser step vs torch.optim.AdamW + clip_grad_norm_ (three steps: the device clock advances inside the op)
+    n = 4096 + 64
+    p0 = torch.randn(n, generator=g).cuda()
+    refp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([refp], lr=3e-3, weight_decay=1e-2)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hyper = torch.tensor([3e-3, 0, 0, 0], device="cuda")
+    sq = torch.zeros(1, device="cuda")
+    for i in range(3):
+        gr = torch.randn(n, generator=g).cuda() * 3
+        refp.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([refp], 1.0)
+        opt.step()
+        gg = gr.clone()
+        torch.ops.tavk.adamw_step(p, m, v, gg, pb, step, hyper, sq, 0.9, 0.999, 1e-8, 1e-2, 1.0, 1.0)
+        assert gg.abs().max().item() == 0.0                       # the update zeroes the gradient
+    assert int(step.item()) == 3
+    assert rel(p, refp.detach()) < 1e-6 and torch.equal(pb.float(), p.bfloat16().float())
+    checks = ("test_schema", "test_faketensor", "test_autograd_registration")
+    torch.library.opcheck(torch.ops.tavk.linear, (x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True),
+                                                  b.detach().clone().requires_grad_(True)), test_utils=checks)
+    torch.library.opcheck(torch.ops.tavk.embed_add, (ours[0].clone().requires_grad_(True), idx, table.detach().clone().requires_grad_(True)),
+                          test_utils=checks)
+    torch.library.opcheck(torch.ops.tavk.dropout, (xd.detach().clone().requires_grad_(True), 0.4, 1234, counter), test_utils=checks)
+    torch.library.opcheck(torch.ops.tavk.adamw_step, (p.clone(), m.clone(), v.clone(), torch.randn(n, device="cuda"), pb.clone(),
+                                                      step.clone(), hyper.clone(), sq.clone(), 0.9, 0.999, 1e-8, 1e-2, 1.0, 1.0),
+                          test_utils=("test_schema", "test_faketensor"))
