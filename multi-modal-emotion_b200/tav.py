@@ -173,14 +173,21 @@ class PreFormer(nn.Module):
         embedded_audio = engine.layer_norm(embedded_audio, enc.layer_norm.weight, enc.layer_norm.bias,
                                            self.wav2vec2.config.layer_norm_eps)
         embedded_audio = engine.linear_bf16(embedded_audio, self.wav_2_768.weight, self.wav_2_768.bias)
-        # video (:368): PreFormer keeps the tokens where visual_mask is True
-        embedded_video = hf.video_embeddings(self.videomae.embeddings, video_embeds, ~visual_mask, keep_count)
+        # video (:368): PreFormer keeps the tokens where visual_mask is True.  video_embeds=None drops the segment: the
+        # restated text+audio configuration (BASELINE configs[2]; the reference's own text+audio model does not parse,
+        # SURVEY Q16 / 8d C3 — "the TAV fused path with the video segment removed")
+        segs = []
         if input_ids is not None:
-            tav = torch.concat((embedded_bert.float(), embedded_audio, embedded_video.float()), dim=1)
-        else:
-            tav = torch.concat((embedded_audio, embedded_video.float()), dim=1)
+            segs.append(embedded_bert.float())
+        segs.append(embedded_audio)
+        K = 0
+        if video_embeds is not None:
+            embedded_video = hf.video_embeddings(self.videomae.embeddings, video_embeds, ~visual_mask, keep_count)
+            segs.append(embedded_video.float())
+            K = embedded_video.shape[1]
+        tav = torch.concat(segs, dim=1)
         # modality ids and additive masks (:381-411), built on device
-        B, Ta, K = embedded_audio.shape[0], embedded_audio.shape[1], embedded_video.shape[1]
+        B, Ta = embedded_audio.shape[0], embedded_audio.shape[1]
         parts, masks = [], []
         if input_ids is not None:
             T = embedded_bert.shape[1]
@@ -190,9 +197,10 @@ class PreFormer(nn.Module):
         parts.append(torch.ones((B, Ta), dtype=torch.long, device=dev))
         if audio_mask is not None:
             masks.append(1.0 - audio_mask[:, None, None, :].float() * _FP16_MIN)  # reference precedence quirk (Q2)
-        parts.append(torch.full((B, K), 2, dtype=torch.long, device=dev))
-        if visual_mask is not None:
-            masks.append(torch.zeros((B, 1, 1, K), dtype=torch.float32, device=dev))
+        if video_embeds is not None:
+            parts.append(torch.full((B, K), 2, dtype=torch.long, device=dev))
+            if visual_mask is not None:
+                masks.append(torch.zeros((B, 1, 1, K), dtype=torch.float32, device=dev))
         tav_embed = torch.concat(parts, dim=1)
         attention_mask = torch.concat(masks, dim=-1)
         if self.check_shapes == 1:
@@ -301,3 +309,59 @@ class TAVForMAE(nn.Module):
         if check == "train":                                                                            # :497-498
             tav = engine.dropout(tav, self.dropout.p)
         return engine.small_linear(tav, self.linear1.weight, self.linear1.bias)                         # :499
+
+
+class TextAudioForMAE(nn.Module):
+    """Restated text+audio fusion classifier (BASELINE configs[2], IEMOCAP-shape long audio).  The reference's own
+    text+audio model (DoubleModels/models/text_audio.py, DoubleModels/text_audio_nn.py) does not parse and imports modules
+    that do not exist, so there is nothing to be a drop-in for: SURVEY 8d (C3) restates it as TAVForMAE with
+    the video segment removed — PreFormer(video_embeds=None) supplies text+audio tokens (S = T + Ta), the head is
+    Linear(3*768, C) over [fusion, text, audio].  Parity is against the oracle's restatement of the same module
+    (oracle.tav_oracle.OracleTAV(with_video=False)) and is flagged "unpinned by reference" in DESIGN.md."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.output_dim = args["output_dim"]
+        self.learn_PosEmbeddings = args["learn_PosEmbeddings"]
+        from transformers import RobertaModel, VideoMAEConfig, Wav2Vec2Model
+
+        c = encoder_configs()
+        self.embedding = nn.Embedding(3, 768)
+        self.embedding.weight.requires_grad = self.learn_PosEmbeddings
+        self.bert, self.wav2vec2 = RobertaModel(c["text"]).eval(), Wav2Vec2Model(c["audio"]).eval()
+        self.bert_norm = nn.LayerNorm(768)
+        self.random_mae_config = VideoMAEConfig()
+        self.random_mae_encoder = VideoMAEEncoder(self.random_mae_config, 12).apply(TAVForMAE.randomize_model.__get__(self))
+        self.rand_norm = nn.LayerNorm(768)
+        self.aud_norm = nn.LayerNorm(768)
+        self.dropout = nn.Dropout(args["dropout"])
+        self.linear1 = nn.Linear(768 * 3, self.output_dim)
+        self.wav_2_768_2 = nn.Linear(self.wav2vec2.config.hidden_size, 768)
+        self.wav_2_768_2.weight = torch.nn.init.xavier_normal_(self.wav_2_768_2.weight)
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in (self.bert, self.wav2vec2):
+            m.eval()
+        return self
+
+    def forward(self, input_ids, text_attention_mask, audio_features, hidden_states, pos_embed, attention_mask, batch_size=2,
+                check="train"):
+        dev = self.linear1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("TextAudioForMAE runs on the sm_100a kernel path only (there is no CPU fallback)")
+        to = lambda t: None if t is None else t.to(dev, non_blocking=True)  # noqa: E731
+        hidden_states, pos_embed, attention_mask = to(hidden_states), to(pos_embed), to(attention_mask)
+        audio_features, input_ids, text_attention_mask = to(audio_features), to(input_ids), to(text_attention_mask)
+        av = engine.embed_add(hidden_states, pos_embed, self.embedding.weight)
+        aud = hf.run_wav2vec2(self.wav2vec2, audio_features)
+        aud = engine.mean_pool(engine.linear_bf16(aud, self.wav_2_768_2.weight, self.wav_2_768_2.bias))
+        _, t = hf.run_roberta(self.bert, input_ids, text_attention_mask)
+        t = engine.layer_norm(t, self.bert_norm.weight, self.bert_norm.bias, self.bert_norm.eps)
+        av = self.random_mae_encoder(av, attention_mask)
+        av = engine.layer_norm(engine.mean_pool(av), self.rand_norm.weight, self.rand_norm.bias, self.rand_norm.eps)
+        aud = engine.layer_norm(aud, self.aud_norm.weight, self.aud_norm.bias, self.aud_norm.eps)
+        out = torch.cat([av, t, aud], dim=1)
+        if check == "train":
+            out = engine.dropout(out, self.dropout.p)
+        return engine.small_linear(out, self.linear1.weight, self.linear1.bias)

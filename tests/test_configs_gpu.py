@@ -86,3 +86,52 @@ def test_tav_baseline_families_vs_oracle(cfg, B):
         print("   largest error contributions: %-70s |d| %.3e  |g| %.3e" % (k, d2 ** 0.5, n2 ** 0.5))
     assert not bad, bad
     assert (num / den) ** 0.5 < 2e-2
+
+
+def test_restated_text_audio_model_c3_shape_vs_oracle():
+    """BASELINE configs[2]: text+audio on IEMOCAP-shape long audio (15 s -> 749 frames, fused S = 70 + 749 = 819).  The
+    reference's own text+audio model does not parse; SURVEY 8d restates it as the TAV fused path without the
+    video segment (tav.TextAudioForMAE over PreFormer(video_embeds=None)).  Parity is against the oracle's restatement of
+    the same module — "unpinned by reference" — with the tolerances of the other configurations."""
+    from multi_modal_emotion_b200 import synthetic as syn, tav
+    from multi_modal_emotion_b200.losses import NewCrossEntropyLoss
+    from oracle import tav_oracle as O
+
+    B = 2
+    tav.set_encoder_variant("tiny_base")
+    torch.manual_seed(0)
+    model = tav.TextAudioForMAE({"output_dim": 7, "dropout": 0.4, "learn_PosEmbeddings": True})
+    pre = tav.PreFormer()
+    pre_sd, sd = syn.synth_state_dict(pre, seed=5), syn.synth_state_dict(model, seed=6)
+    pre.load_state_dict(pre_sd)
+    model.load_state_dict(sd)
+    model, pre = model.cuda(), pre.cuda()
+    inputs, labels = syn.make_batch("C3", seed=7, B=B)
+    ids, tm = inputs[0]["input_ids"].cuda(), inputs[0]["attention_mask"].cuda()
+    wav, am = inputs[1]["audio_features"].cuda(), inputs[1]["attention_mask"].cuda()
+    w = torch.tensor(syn.MELD_CLASS_WEIGHTS)
+    crit = NewCrossEntropyLoss(class_weights=w, epoch_switch=2)
+    t, pos, mask = pre(input_ids=ids, audio_features=wav, video_embeds=None, text_mask=tm, audio_mask=am, visual_mask=None,
+                       device="cuda", train=False)
+    assert t.shape[1] == 70 + syn.conv_frames(syn.CONFIGS["C3"]["L"]) == 819 and mask.shape == (B, 1, 1, 819)
+    logits = model(ids, tm, wav, t, pos, mask, batch_size=B, check="val")
+    loss = crit(logits, labels.cuda().long(), epoch=1)
+    loss.backward()
+    grads = {}
+    for tag, m in (("TAVForMAE", model), ("PreFormer", pre)):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                grads["%s/%s" % (tag, k)] = p.grad
+    orc = O.OracleTAV(tav.encoder_configs("tiny_base"), with_video=False).load(pre_sd, sd)
+    lo = orc.forward_text_audio(inputs)
+    loss_o = O.new_cross_entropy(lo, labels.long(), 1, w, 2)
+    loss_o.backward()
+    og = orc.named_grads()
+    err = (logits.detach().cpu() - lo.detach()).abs().max().item()
+    assert set(og) == set(grads)
+    num = sum((grads[k].cpu() - g).norm().item() ** 2 for k, g in og.items())
+    den = sum(g.norm().item() ** 2 for g in og.values())
+    print("restated text+audio, C3 shape (S=819): logits max abs err %.3e, loss %.6f vs %.6f, flat gradient rel-L2 %.3e over %d tensors"
+          % (err, loss.item(), loss_o.item(), (num / den) ** 0.5, len(og)))
+    assert err < 3e-2 and abs(loss.item() - loss_o.item()) < 2e-2
+    assert (num / den) ** 0.5 < 2e-2
