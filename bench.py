@@ -39,6 +39,10 @@ def parse():
     ap.add_argument("--recompute", action="store_true",
                     help="selective recompute: keep only layer inputs, re-run each layer's forward in backward (large batches)")
     ap.add_argument("--no-fusion-128", action="store_true", help="skip the extra 128-sample fusion-block measurement")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-signature GEMM roofline and fusion-block legs (sweeps)")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="gradient all-reduce bucket size")
+    ap.add_argument("--grad-reduce", default="fp32", choices=["fp32", "bf16"],
+                    help="dtype of the gradient all-reduce (bf16 = opt-in compression; default exact fp32 sums)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples per CPU-baseline step (bounded sample)")
     return ap.parse_args()
 
@@ -355,7 +359,8 @@ def main():
     crit = NewCrossEntropyLoss(torch.tensor(syn.MELD_CLASS_WEIGHTS if C == 7 else [0.5, 0.5]), epoch_switch=2)
     params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
     opt = FusedAdamW(params, lr=1e-5, weight_decay=1e-4)
-    runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=32, use_cuda_graph=not args.no_graph)
+    runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=args.bucket_mb, use_cuda_graph=not args.no_graph,
+                                grad_reduce_dtype=torch.bfloat16 if args.grad_reduce == "bf16" else None)
 
     host_inputs, host_labels = syn.make_batch(cfg, seed=1234 + rank, B=B)
     host_inputs = [{k: v.pin_memory() for k, v in d.items()} for d in host_inputs]
@@ -430,7 +435,7 @@ def main():
 
     line = None
     if rank == 0:
-        roof, fusion = roofline_and_fusion(torch, L, syn, model, B, cfg, ms_max, peaks)
+        roof, fusion = (None, None) if args.no_roofline else roofline_and_fusion(torch, L, syn, model, B, cfg, ms_max, peaks)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -440,7 +445,7 @@ def main():
                        "parallelism": "dp%d" % world, "cuda_graph": not args.no_graph,
                        "l2_policy": "inputs (%.0f MB/step) and saved activations exceed the 126 MB L2; no explicit flush" % (h2d / 1e6),
                        "step": "fwd + loss + bwd + grad all-reduce + clip + AdamW",
-                       "activation_recompute": bool(args.recompute)},
+                       "activation_recompute": bool(args.recompute), "grad_all_reduce": "%s, %d MB buckets" % (args.grad_reduce, args.bucket_mb)},
             "e2e": {"value": B * world / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e,
                     "how": "train_step(host batch, next_batch=...): pinned-host H2D of every batch (copy of batch i+1 "
