@@ -40,7 +40,7 @@ def parse():
                     help="selective recompute: keep only layer inputs, re-run each layer's forward in backward (large batches)")
     ap.add_argument("--no-fusion-128", action="store_true", help="skip the extra 128-sample fusion-block measurement")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-signature GEMM roofline and fusion-block legs (sweeps)")
-    ap.add_argument("--bucket-mb", type=int, default=32, help="gradient all-reduce bucket size")
+    ap.add_argument("--bucket-mb", type=int, default=128, help="gradient all-reduce bucket size (measured at 2 GPUs: 128 MB 43.6 ms/step, 32 MB 44.8)")
     ap.add_argument("--grad-reduce", default="fp32", choices=["fp32", "bf16"],
                     help="dtype of the gradient all-reduce (bf16 = opt-in compression; default exact fp32 sums)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples per CPU-baseline step (bounded sample)")

@@ -137,7 +137,7 @@ class DataParallelTAV:
     """Drives one data-parallel training step of (PreFormer, TAVForMAE): forward on the local shard, global-loss
     normalisation, backward overlapped with bucketed gradient all-reduce, fused clip + AdamW on identical gradients."""
 
-    def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=32, group=None,
+    def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=128, group=None,
                  use_cuda_graph=False, graph_warmup=3, scheduler=None, grad_reduce_dtype=None):
         """``scheduler``: the reference's CosineAnnealingWarmRestarts (or any torch scheduler over ``optimizer``).
         ``train_step(..., sched_t=epoch + i/iters)`` steps it after the update exactly like the reference loop

@@ -104,5 +104,7 @@ def test_two_nccl_ranks_reproduce_the_single_process_step(tmp_path):
         print("step %d: whole-model flat gradient rel-L2 %.2e; worst tensor %.2e (%s)" % (i + 1, (num / den) ** 0.5, worst[0], worst[1]))
         assert (num / den) ** 0.5 < 2e-2
         for e, k in errs:
+            if k.endswith("key.bias") or k.endswith("k_proj.bias"):
+                continue    # exact gradient is ZERO (softmax is invariant to a constant added to every key's score): pure noise
             qk = any(t in k for t in (".query.", ".key.", ".q_proj.", ".k_proj."))
             assert e < (2.5e-1 if qk else 5e-2), (k, e)
