@@ -115,6 +115,10 @@ typedef struct tavk_gemm_args {
      * counter: a CTA whose SM is still held by another stream's kernel or an NCCL collective claims fewer tiles
      * instead of holding the whole grid back. */
     void* sched_workspace;
+    /* CTA pairs (tcgen05 cta_group::2: two CTAs of one cluster share a 256-row output tile and each loads half of the B
+     * tile): 0 = the library decides (plain problems with >= 4 row blocks), 1 = never, 2 = whenever the problem allows it
+     * (ungrouped, no convolution walk, N > 64, M > 128).  Pair launches use the static tile order (sched_workspace unused). */
+    int32_t cta_pair;
 } tavk_gemm_args;
 int tavk_gemm_bf16(const tavk_gemm_args* args, void* stream);
 

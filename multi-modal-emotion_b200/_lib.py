@@ -41,6 +41,7 @@ class GemmArgs(C.Structure):
         ("a_rows", C.c_int64), ("a_cols", C.c_int64), ("b_rows", C.c_int64), ("b_cols", C.c_int64),
         ("max_ctas", C.c_int32),
         ("sched_workspace", C.c_void_p),
+        ("cta_pair", C.c_int32),
     ]
 
 
@@ -212,7 +213,7 @@ _GEMM_EXT = ("groups", "a_kstep", "a_g_mn", "a_g_k", "b_g_mn", "b_g_k", "b_box_k
 
 def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2=None, bias=None, resid=None,
          rowbias=None, rows_per_group=0, aux=None, colsum=None, epilogue=EPI_LINEAR, accumulate=False, k_splits=1,
-         block_n=0, alpha=1.0, ldo=None, **ext):
+         block_n=0, alpha=1.0, ldo=None, cta_pair=0, **ext):
     """out[M,N] = epi(alpha * A·B^T).  A/B bf16 2-D tensors (or views); K-major: [rows,K]; MN-major: [K,rows].
     ``ext``: the grouped / convolution-walk fields of tavk_gemm_args (groups, a_kstep, a_g_mn, ..., b_cols)."""
     a = GemmArgs()
@@ -232,6 +233,7 @@ def gemm(A, B, out, *, M, N, K, lda=None, ldb=None, a_mn=False, b_mn=False, out2
     a.aux, a.ldaux = _ptr(aux), (aux.stride(0) if aux is not None else 0)
     a.colsum = _ptr(colsum)
     a.epilogue, a.accumulate, a.k_splits, a.block_n, a.alpha = epilogue, int(accumulate), k_splits, block_n, alpha
+    a.cta_pair = cta_pair      # 0 = library heuristic, 1 = single-CTA tiles, 2 = CTA pairs (cta_group::2) when possible
     if gemm_reserved_sms:
         a.max_ctas = lib().tavk_sm_count() - gemm_reserved_sms
     if gemm_dynamic_tiles:

@@ -53,6 +53,27 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Same for a kernel that runs as clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  unsigned cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (device side)
 // Blocks until the predecessor grid has completed and its memory is visible (no-op without the launch attribute).
 TAVK_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -314,6 +335,43 @@ TAVK_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int line = __
     }
 }
 
+// ---------------------------------------------------------------- CTA pair (cluster of two, tcgen05 cta_group::2)
+TAVK_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// every thread of both CTAs
+TAVK_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+TAVK_DEVINL uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+TAVK_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier of this CTA whose arrivals come from the peer CTA too
+TAVK_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int line = __builtin_LINE()) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) mbar_timeout_report(line);
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 TAVK_DEVINL void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -322,6 +380,14 @@ TAVK_DEVINL void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, in
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// Same from a CTA of a pair (tcgen05 cta_group::2): the bytes land in THIS CTA's shared memory, the complete_tx goes to the
+// barrier at shared::cluster address `bar_cluster` — the leader CTA's full barrier, which its MMA issuer waits on.
+TAVK_DEVINL void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
 }
 TAVK_DEVINL void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
@@ -386,6 +452,37 @@ TAVK_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 TAVK_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// ---- CTA-pair forms (cta_group::2): one warp of EACH CTA of the pair allocates / frees; only the leader CTA (cluster rank
+// 0) issues MMAs — D is 256 rows (128 TMEM lanes in each CTA) x N columns, A = each CTA's own 128-row tile, B = N/2 rows
+// from each CTA's shared memory at the same offset — and its commits arrive on the barrier at the same offset in both CTAs.
+template <uint32_t kCols>
+TAVK_DEVINL void tmem_alloc_pair(uint32_t* smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+TAVK_DEVINL void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(kCols) : "memory");
+}
+TAVK_DEVINL void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+TAVK_DEVINL void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane i of the warp's quarter).

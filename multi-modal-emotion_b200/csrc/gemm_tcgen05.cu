@@ -11,6 +11,14 @@
 //                 row-bias / column-sum -> global)
 //   smem ring of kStages {A tile 128x64, B tile BLOCK_Nx64}; TMEM double-buffered accumulator so the
 //   epilogue of tile i overlaps the MMA main loop of tile i+1.
+// CTA-pair mode (template CTAS = 2, tcgen05 cta_group::2): the grid is launched as clusters of two CTAs (one TPC); a pair
+//   owns a 256 x BLOCK_N output tile.  Each CTA loads its own 128 rows of A and HALF of the B tile (BLOCK_N/2 rows), the
+//   leader CTA's warp 1 issues UMMA 256 x BLOCK_N x 16 which reads B from both CTAs' shared memory, and each CTA's TMEM
+//   receives its 128 rows.  Per CTA and k-block that is 32 KB instead of 48 KB of TMA traffic and shared-memory fill, and
+//   the ring is 6 deep instead of 4 (1.5x more k in flight per SM), which is what the single-CTA main loop was short of.
+//   Barriers: both CTAs' TMA loads complete_tx on the LEADER's full barrier (armed with the bytes of both), the MMA
+//   commits multicast to the empty / tmem_full barriers of both CTAs, and the peer's epilogue warps release the
+//   accumulator with a remote arrive on the leader's tmem_empty barrier.  Static tile order (no dynamic scheduler).
 // K-major operand tile  : one TMA box {64 k, rows}; UMMA desc SBO = 1024 B, K advance = +32 B per UMMA_K.
 // MN-major operand tile : rows/64 TMA boxes {64 mn, 64 k}; UMMA desc LBO = 8192 B (next 64-wide MN group),
 //                         SBO = 1024 B (next 8 k rows), K advance = +2048 B per UMMA_K.
@@ -27,11 +35,13 @@ constexpr int kUmmaK = 16;
 constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 struct GemmCfg {
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static_assert(CTAS == 1 || (CTAS == 2 && BLOCK_N >= 128), "CTA pairs: BLOCK_N 128 or 256");
+    static constexpr int kBRows = BLOCK_N / CTAS;           // rows of the B tile THIS CTA loads
+    static constexpr int kStages = CTAS == 2 ? (BLOCK_N == 256 ? 6 : 8) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
     static constexpr int kABytes = kBlockM * kBlockK * 2;
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (128, 256 or 512 columns)
     static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // one 32x32 fp32 transpose patch per epilogue warp
@@ -40,6 +50,7 @@ struct GemmCfg {
 
 struct GemmDev {
     int M, N, K;
+    int m_tile;                     // output rows per tile: 128, or 256 for a CTA pair (each CTA owns 128 of them)
     int num_m_blocks, num_n_blocks, k_splits, kb_per_split, num_kb;
     void* out;
     long long ldo;
@@ -91,9 +102,10 @@ struct TileSrc {
     uint64_t* full;
     uint64_t* empty;
     int num_tiles, lane;
+    int first, stride;                      // static order: this CTA's (pair's) first tile and the number of CTAs (pairs)
     TAVK_DEVINL int get(int i) const {      // whole warp
         if (sched == nullptr) {
-            const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+            const long long t = (long long)first + (long long)i * stride;
             return t < num_tiles ? (int)t : -1;
         }
         const int slot = i & (kSchedDepth - 1);
@@ -129,8 +141,9 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
     o.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias != nullptr && w.lead && (FULL || w.col_ok)) o.b4 = __ldg(reinterpret_cast<const float4*>(p.bias + w.col));
     if (MODE == TAVK_EPI_LINEAR) {
-        const bool use_res = p.resid != nullptr && w.lead;
-        const bool use_rb = p.rowbias != nullptr && w.lead;
+        const bool any = FULL || w.rows_valid > 0;      // a CTA pair's lower half may lie entirely past M
+        const bool use_res = p.resid != nullptr && w.lead && any;
+        const bool use_rb = p.rowbias != nullptr && w.lead && any;
         if (use_res) {
             const float* rp = p.resid + (long long)(w.row_base + rsub) * p.ldr + w.col;
             const long long rstep = 4 * p.ldr;
@@ -180,16 +193,20 @@ TAVK_DEVINL void epi_issue_loads(const GemmDev& p, const EpiItem& w, int rsub, E
 
 template <int MODE, int OUT, bool FULL>
 TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperands<MODE>& o, uint32_t taddr, uint32_t stg,
-                             int lane, uint64_t* release_bar) {
+                             int lane, uint64_t* release_bar, uint32_t release_remote) {
     const int cc = lane & 7, rsub = lane >> 3;
     uint32_t r[32];
     tmem_ld_32x32(taddr, r);
     tmem_ld_wait();
     if (release_bar != nullptr) {
         // last chunk of the tile for this warp: hand the TMEM buffer back to the MMA issuer before the global stores
+        // (release_remote: this is the peer CTA of a pair — the issuer's barrier lives in the leader's shared memory)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(release_bar);
+        if (lane == 0) {
+            if (release_remote != 0) mbar_arrive_cluster(release_remote);
+            else mbar_arrive(release_bar);
+        }
     }
     if (p.debug == 1) return;       // measurement: main loop + TMEM drain only
     const uint32_t st_addr = stg + lane * 128;
@@ -292,7 +309,8 @@ TAVK_DEVINL void epi_process(const GemmDev& p, const EpiItem& w, const EpiOperan
 
 template <int BLOCK_N, int MODE, int OUT>
 TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t stg, int lane, int quarter, int half,
-                               const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+                               const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int row_off,
+                               uint32_t empty_remote) {
     constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     const int cc = lane & 7, rsub = lane >> 3;
     // per TILE (integer divisions live here, not in the per-chunk path): everything but the chunk's column
@@ -303,7 +321,7 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         const int tg = tile - g * p.tiles_per_group;
         const int mn = tg / p.k_splits;
         const int m_blk = mn / p.num_n_blocks;
-        const int row_local = m_blk * kBlockM + quarter * 32;
+        const int row_local = m_blk * p.m_tile + row_off + quarter * 32;     // row_off: 128 in the peer CTA of a pair
         const int col_chunk = (mn - m_blk * p.num_n_blocks) * BLOCK_N + half * 32;      // warp-uniform
         t.lead = (tg - mn * p.k_splits) == 0;
         t.rows_valid = p.M - row_local;
@@ -359,8 +377,9 @@ TAVK_DEVINL void epilogue_loop(const GemmDev& p, uint32_t tmem_base, uint32_t st
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + (half + 2 * ci) * 32);
         const bool last = (ci == kPer - 1);
         uint64_t* rel = last ? &tmem_empty_bar[acc] : nullptr;
-        if (w_cur.full) epi_process<MODE, OUT, true>(p, w_cur, op_cur, taddr, stg, lane, rel);
-        else epi_process<MODE, OUT, false>(p, w_cur, op_cur, taddr, stg, lane, rel);
+        const uint32_t rel_remote = empty_remote != 0 ? empty_remote + 8u * (uint32_t)acc : 0u;
+        if (w_cur.full) epi_process<MODE, OUT, true>(p, w_cur, op_cur, taddr, stg, lane, rel, rel_remote);
+        else epi_process<MODE, OUT, false>(p, w_cur, op_cur, taddr, stg, lane, rel, rel_remote);
         if (last) ++it;
         if (!more) break;
         if (nci == 0) {                     // advanced to the next tile: fetch the one after it
@@ -390,7 +409,8 @@ TAVK_DEVINL uint32_t sw64_off(int row, int chunk16) {      // byte offset of 16-
 template <int BLOCK_N, int MODE>
 TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2,
                                    const CUtensorMap* tmap_aux, uint32_t tmem_base, uint8_t* stg, uint64_t* aux_bar, int lane,
-                                   int quarter, int half, const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
+                                   int quarter, int half, const TileSrc& src, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                   int row_off, uint32_t empty_remote) {
     constexpr int kPer = BLOCK_N / 64;      // chunks per warp per tile (1, 2 or 4)
     constexpr bool kGelu = (MODE == TAVK_EPI_GELU || MODE == TAVK_EPI_GELU_GRAD);
     constexpr bool kAux = (MODE == TAVK_EPI_GELU_BWD || MODE == TAVK_EPI_MUL);
@@ -399,7 +419,7 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
     auto coords = [&](int tile, int ci, int& row0, int& col0) {
         const int mn = tile / p.k_splits;                    // k_splits == 1 on this path, groups == 1
         const int m_blk = mn / p.num_n_blocks;
-        row0 = m_blk * kBlockM + quarter * 32;
+        row0 = m_blk * p.m_tile + row_off + quarter * 32;
         col0 = (mn - m_blk * p.num_n_blocks) * BLOCK_N + (half + 2 * ci) * 32;
     };
     int i_tile = 0, ci = 0, it = 0, n_item = 0;
@@ -445,7 +465,10 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
             // last chunk of the tile for this warp: hand the TMEM buffer back to the MMA issuer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (empty_remote != 0) mbar_arrive_cluster(empty_remote + 8u * (uint32_t)acc);
+                else mbar_arrive(&tmem_empty_bar[acc]);
+            }
             ++it;
         }
         if (p.debug == 1) {
@@ -546,12 +569,14 @@ TAVK_DEVINL void epilogue_loop_tma(const GemmDev& p, const CUtensorMap* tmap_out
     __syncwarp();
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                          const __grid_constant__ CUtensorMap tmap_aux, const GemmDev p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, CTAS>;
+    constexpr bool kPair = CTAS == 2;
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs of the pair)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -581,7 +606,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+            mbar_init(&tmem_empty_bar[i], kNumEpiWarps * CTAS);     // pair: the peer's epilogue warps arrive remotely
         }
         for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
         for (int i = 0; i < kSchedDepth; ++i) {
@@ -595,14 +620,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         mbar_fence_init();
     }
-    if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+    if (warp_idx == 1) {
+        if constexpr (kPair) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_smem);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();    // the peer's barriers exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
     const int num_tiles = p.groups * p.tiles_per_group;
-    const TileSrc src{p.sched, sched_ring, sched_full, sched_empty, num_tiles, lane};
+    const TileSrc src{kPair ? nullptr : p.sched, sched_ring, sched_full, sched_empty, num_tiles, lane,
+                      kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x};
+    const int row_off = (int)cta_rank * kBlockM;
     pdl_trigger();   // the next kernel on the stream may start its own prologue ...
     pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
 
@@ -613,8 +644,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             // tile i of this CTA: static round robin, or claimed from the global counter and published one tile ahead
             auto claim = [&](int i) -> int {
-                if (p.sched == nullptr) {
-                    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+                if (src.sched == nullptr) {
+                    const long long t = (long long)src.first + (long long)i * src.stride;
                     return t < num_tiles ? (int)t : -1;
                 }
                 const int c = atomicAdd(p.sched, 1);
@@ -636,13 +667,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int m_blk = mn / p.num_n_blocks;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-                const int a_mn0 = m_blk * kBlockM + g * p.a_g_mn, a_k0 = g * p.a_g_k;
+                const int a_mn0 = m_blk * p.m_tile + row_off + g * p.a_g_mn, a_k0 = g * p.a_g_k;
                 const int b_k0 = g * p.b_g_k;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     uint8_t* sa = smem_a + stage * Cfg::kABytes;
                     uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+                    if constexpr (kPair) {
+                        // both CTAs' loads of this stage complete on the leader's barrier, armed with the bytes of both
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if constexpr (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < kBlockM / 64; ++j)
+                                tma_load_2d_pair(sa + j * 8192, &tmap_a, fb, a_mn0 + j * 64, a_k0 + kb * kBlockK);
+                        } else {
+                            tma_load_2d_pair(sa, &tmap_a, fb, a_k0 + kb * kBlockK, a_mn0);
+                        }
+                        const int b_mn0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;    // this CTA's half of the B tile
+                        if constexpr (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < Cfg::kBRows / 64; ++j)
+                                tma_load_2d_pair(sb + j * 8192, &tmap_b, fb, b_mn0 + j * 64, b_k0 + kb * kBlockK);
+                        } else {
+                            tma_load_2d_pair(sb, &tmap_b, fb, b_k0 + kb * kBlockK, b_mn0);
+                        }
+                        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     if constexpr (A_MN) {
 #pragma unroll
                         for (int j = 0; j < kBlockM / 64; ++j)
@@ -664,7 +717,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 tile = tile_after;
             }
-            if (p.sched != nullptr) {
+            if (src.sched != nullptr) {
                 // last CTA to finish claiming resets the workspace for the next launch that uses it
                 __threadfence();
                 if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
@@ -674,10 +727,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
         }
-    } else if (warp_idx == 1) {
+    } else if (warp_idx == 1 && cta_rank == 0) {
         // ===================== MMA issuer: the whole warp walks the (warp-uniform) loop, one elected lane issues ====
+        // (of a CTA pair only the leader's warp 1 comes here; the peer's only allocates and frees its tensor memory)
         const bool leader = elect_one();
-        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, A_MN, B_MN);
+        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CTAS, BLOCK_N, A_MN, B_MN);
         const uint64_t da0 = A_MN ? umma_smem_desc(smem_u32(smem_a), 8192, 1024) : umma_smem_desc(smem_u32(smem_a), 16, 1024);
         const uint64_t db0 = B_MN ? umma_smem_desc(smem_u32(smem_b), 8192, 1024) : umma_smem_desc(smem_u32(smem_b), 16, 1024);
         constexpr uint64_t kAStep = A_MN ? (2048 >> 4) : (32 >> 4);   // descriptor address units (16 B) per UMMA_K
@@ -691,7 +745,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            if constexpr (kPair) mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+            else mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -701,27 +756,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint64_t da = da0 + (uint64_t)(stage * (Cfg::kABytes >> 4));
                     const uint64_t db = db0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_bf16(tmem_d, da + k * kAStep, db + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        if constexpr (kPair) umma_bf16_pair(tmem_d, da + k * kAStep, db + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + k * kAStep, db + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (kPair) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
-            if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+            if (leader) {   // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]);
+                else umma_commit(&tmem_full_bar[acc]);
+            }
             __syncwarp();
         }
-    } else {
+    } else if (warp_idx >= 2) {
         // ===================== epilogue warps =====================
         const int ew = warp_idx - 2;            // 0..7
         const int quarter = warp_idx & 3;       // TMEM lane quarter this warp may access
         const int half = ew >> 2;               // which half of the column chunks
         const uint32_t stg = smem_u32(smem_stage) + ew * 4096;
+        // peer CTA of a pair: the accumulator is released on the leader's tmem_empty barriers
+        const uint32_t empty_remote = (kPair && cta_rank != 0) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
 #define TAVK_EPI_TMA(MODE)                                                                                             \
     epilogue_loop_tma<BLOCK_N, MODE>(p, &tmap_out, &tmap_out2, &tmap_aux, tmem_base, smem_stage + ew * 4096, &aux_bar[ew], lane, \
-                                     quarter, half, src, tmem_full_bar, tmem_empty_bar)
+                                     quarter, half, src, tmem_full_bar, tmem_empty_bar, row_off, empty_remote)
 #define TAVK_EPI(MODE, OUT) \
-    epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, src, tmem_full_bar, tmem_empty_bar)
+    epilogue_loop<BLOCK_N, MODE, OUT>(p, tmem_base, stg, lane, quarter, half, src, tmem_full_bar, tmem_empty_bar, row_off, empty_remote)
         if (p.tma_epi) {
             if (p.epilogue == TAVK_EPI_GELU) TAVK_EPI_TMA(TAVK_EPI_GELU);
             else if (p.epilogue == TAVK_EPI_GELU_GRAD) TAVK_EPI_TMA(TAVK_EPI_GELU_GRAD);
@@ -740,11 +804,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
 
     tc_fence_before();
-    __syncthreads();
+    // pair: neither CTA may leave (or free tensor memory) while the other can still signal its barriers, read its shared
+    // memory through the MMA, or drain its half of the accumulator
+    if constexpr (kPair) cluster_sync_all();
+    else __syncthreads();
     if (warp_idx == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
@@ -782,17 +850,20 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, long long rows, lo
     return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CTAS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const CUtensorMap& tx, const GemmDev& dev, int grid, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
-    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+    using Cfg = GemmCfg<BLOCK_N, CTAS>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CTAS>;
     static bool attr_done = false;
     if (!attr_done) {
         TAVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    TAVK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, to, to2, tx, dev));
+    if (CTAS == 2)
+        TAVK_CUDA(launch_kernel_cluster(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, 2u, ta, tb, to, to2, tx, dev));
+    else
+        TAVK_CUDA(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, to, to2, tx, dev));
     return 0;
 }
 
@@ -832,7 +903,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
 
     // tile-shape heuristic: the widest tile whose wave quantisation is not noticeably worse than a narrower one's
     // per-call SM budget (a data-parallel host keeps a few SMs free for concurrently running NCCL kernels)
-    const int sms = (a->max_ctas > 0 && a->max_ctas < sm_count()) ? a->max_ctas : sm_count();
+    int sms = (a->max_ctas > 0 && a->max_ctas < sm_count()) ? a->max_ctas : sm_count();
     const int mblocks = (a->M + kBlockM - 1) / kBlockM;
     auto waves_eff = [&](int bn) {
         const long long tiles = (long long)groups * mblocks * ((a->N + bn - 1) / bn) * k_splits;
@@ -843,10 +914,25 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     if (a->block_n == 64 || a->block_n == 128 || a->block_n == 256) block_n = a->block_n;
     else if (a->N <= 64) block_n = 64;
     else if (a->N <= 128 || waves_eff(128) > waves_eff(256) * 1.15) block_n = 128;
+    // CTA pairs (cta_group::2, 256-row tiles): plain ungrouped problems with at least two row blocks.  The CTA count and
+    // its wave quantisation are those of the single-CTA tiling (a pair = two CTAs = two 128-row blocks), except for the
+    // idle lower half of the last pair when the number of row blocks is odd.  a->cta_pair: 0 heuristic, 1 never, 2 force.
+    static const int pair_env = getenv("TAVK_GEMM_PAIR") ? atoi(getenv("TAVK_GEMM_PAIR")) : -1;     // 0 = off (measurement)
+    const bool pair_ok = groups == 1 && a->a_kstep == 0 && a->b_box_k_shift == 0 && block_n >= 128 && mblocks >= 2 && sms >= 2;
+    const int pair_req = pair_env >= 0 ? (pair_env ? 0 : 1) : a->cta_pair;
+    // heuristic (tools/gemm_pair_probe.py, profiles/r2_gemm_pair_probe.txt): pairs win 5-15 % once the problem has at least
+    // a wave of single-CTA tiles (and already at half a wave for the split-K wgrad shapes); below that the launch is one
+    // partial wave either way and the pair's cluster scheduling + second barrier hop cost ~0.5 us
+    const long long tiles1 = (long long)mblocks * ((a->N + block_n - 1) / block_n) * k_splits;
+    const bool pair_auto = tiles1 >= sms || (a->a_mn_major && a->b_mn_major && 2 * tiles1 >= sms);
+    const bool pair = pair_ok && pair_req != 1 && (pair_req == 2 || pair_auto);
+    const int ctas = pair ? 2 : 1;
+    if (pair) sms &= ~1;
 
     GemmDev d;
     d.M = a->M; d.N = a->N; d.K = a->K;
-    d.num_m_blocks = mblocks;
+    d.m_tile = kBlockM * ctas;
+    d.num_m_blocks = (a->M + d.m_tile - 1) / d.m_tile;
     d.num_n_blocks = (a->N + block_n - 1) / block_n;
     d.num_kb = (a->K + kBlockK - 1) / kBlockK;
     d.k_splits = k_splits > d.num_kb ? d.num_kb : k_splits;
@@ -861,7 +947,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     d.epilogue = a->epilogue; d.accumulate = a->accumulate; d.alpha = a->alpha;
     static const int dbg = getenv("TAVK_GEMM_DEBUG") ? atoi(getenv("TAVK_GEMM_DEBUG")) : 0;
     d.debug = dbg;
-    d.sched = reinterpret_cast<int*>(a->sched_workspace);
+    d.sched = pair ? nullptr : reinterpret_cast<int*>(a->sched_workspace);
     d.groups = groups;
     d.tiles_per_group = d.num_m_blocks * d.num_n_blocks * d.k_splits;
     d.a_kstep = a->a_kstep > 0 ? a->a_kstep : kBlockK;
@@ -882,7 +968,7 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     else               rc = make_tmap_bf16(&ta, a->A, a_rows, a_cols, a->lda, kBlockK, kBlockM);
     if (rc) return rc;
     if (a->b_mn_major) rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, 64, kBlockK);
-    else               rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, kBlockK, block_n);
+    else               rc = make_tmap_bf16(&tb, a->B, b_rows, b_cols, a->ldb, kBlockK, block_n / ctas);
     if (rc) return rc;
 
     // TMA-store epilogue (see epilogue_loop_tma): plain bf16 outputs of one ungrouped problem
@@ -907,15 +993,19 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
         }
     }
 
-    const long long tiles = (long long)d.groups * d.tiles_per_group;
-    const int grid = (int)(tiles < sms ? tiles : sms);
-#define TAVK_GEMM_DISPATCH(BN)                                                                   \
-    if (a->a_mn_major && a->b_mn_major) return launch_gemm<BN, true, true>(ta, tb, to, to2, tx, d, grid, stream);   \
-    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN, true, false>(ta, tb, to, to2, tx, d, grid, stream); \
-    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN, false, true>(ta, tb, to, to2, tx, d, grid, stream); \
-    return launch_gemm<BN, false, false>(ta, tb, to, to2, tx, d, grid, stream);
-    if (block_n == 256) { TAVK_GEMM_DISPATCH(256) }
-    if (block_n == 128) { TAVK_GEMM_DISPATCH(128) }
-    TAVK_GEMM_DISPATCH(64)
+    const long long tiles = (long long)d.groups * d.tiles_per_group;        // pair mode: 256-row tiles, two CTAs each
+    const int grid = (int)(tiles * ctas < sms ? tiles * ctas : sms);
+#define TAVK_GEMM_DISPATCH(BN, CT)                                                                   \
+    if (a->a_mn_major && a->b_mn_major) return launch_gemm<BN, true, true, CT>(ta, tb, to, to2, tx, d, grid, stream);   \
+    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN, true, false, CT>(ta, tb, to, to2, tx, d, grid, stream); \
+    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN, false, true, CT>(ta, tb, to, to2, tx, d, grid, stream); \
+    return launch_gemm<BN, false, false, CT>(ta, tb, to, to2, tx, d, grid, stream);
+    if (pair) {
+        if (block_n == 256) { TAVK_GEMM_DISPATCH(256, 2) }
+        TAVK_GEMM_DISPATCH(128, 2)
+    }
+    if (block_n == 256) { TAVK_GEMM_DISPATCH(256, 1) }
+    if (block_n == 128) { TAVK_GEMM_DISPATCH(128, 1) }
+    TAVK_GEMM_DISPATCH(64, 1)
 #undef TAVK_GEMM_DISPATCH
 }

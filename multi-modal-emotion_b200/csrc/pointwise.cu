@@ -298,7 +298,9 @@ small_linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict_
     for (int j = 0; j < kSlRows; ++j)
         if (m0 + j < M) atomicAdd(dx + (size_t)(m0 + j) * K + k, acc[j]);
 }
-// dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n, 4 consecutive k) when K % 4 == 0
+// dw[n,k] += sum_m dy[m,n] x[m,k]; db[n] += sum_m dy[m,n]; one thread per (n, 4 consecutive k) when K % 4 == 0.
+// The accumulation into dw / db is atomic (red.global.add): the layer engine runs this next to the tensor-core wgrad GEMM
+// that adds the main term into the same gradient buffer from another stream.
 __global__ void __launch_bounds__(128)
 small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
                           float* __restrict__ db, int M, int N, int K) {
@@ -317,12 +319,10 @@ small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict_
             s.x += d * a.x; s.y += d * a.y; s.z += d * a.z; s.w += d * a.w;
             sb += d;
         }
-        if (dw) {
-            float4* o = reinterpret_cast<float4*>(dw + (size_t)n * K + k);
-            float4 v = *o;
-            v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
-            *o = v;
-        }
+        if (dw)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + (size_t)n * K + k), "f"(s.x), "f"(s.y),
+                         "f"(s.z), "f"(s.w)
+                         : "memory");
     } else {
         float s = 0.f;
         for (int m = 0; m < M; ++m) {
@@ -330,9 +330,9 @@ small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict_
             s += d * x[(size_t)m * K + k];
             sb += d;
         }
-        if (dw) dw[(size_t)n * K + k] += s;
+        if (dw) atomicAdd(dw + (size_t)n * K + k, s);
     }
-    if (db && k == 0) db[n] += sb;
+    if (db && k == 0) atomicAdd(db + n, sb);
 }
 
 // ---------------------------------------------------------------- casts / scaling / dropout

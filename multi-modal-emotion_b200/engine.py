@@ -196,6 +196,47 @@ def _attention_fwd(spec, qkv, B, S, key_bias):
     return o, lse
 
 
+# The rank-1 path of the fusion attention — weighted column sums and three tiny fp32 linears over [B, H] — is
+# latency, not work: ~6 short kernels per layer that depend only on V (forward) or dx1 (backward) and are needed again at
+# the out-projection / the dK/dV kernel.  They run on a side stream next to the attention forward (forward) and next to
+# the out-projection wgrad + dgrad GEMMs (backward) instead of between them; a CUDA-graph capture records the fork and
+# join as dependencies.  Buffers are allocated on the calling stream before the fork and every use of them on the side
+# stream is joined back before the calling stream touches or frees them, so the caching allocator needs no record_stream.
+rank1_side_stream = os.environ.get("TAVK_RANK1_SIDE", "1") != "0"
+_RANK1_STREAMS = {}
+
+
+class _SideWork:
+    """with _SideWork(dev): kernels enqueued inside run on the device's rank-1 side stream, after everything enqueued so
+    far on the calling stream; join() makes the calling stream wait for them."""
+
+    def __init__(self, dev):
+        self.main = torch.cuda.current_stream(dev)
+        self.side = None
+        if rank1_side_stream:
+            self.side = _RANK1_STREAMS.get(dev)
+            if self.side is None:
+                self.side = _RANK1_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=-1)
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 debug_dropout_masks = None   # tests set this to a list: every keep-mask drawn by the layer engine is appended (uint8)
 
 
@@ -237,14 +278,17 @@ def _layer_fwd(spec, p, sh, x, x_bf, B, S, mask2d, keep, li=0, same_as_training=
         h1, _, mean1, rstd1 = L.layernorm_fwd(x, d["ln1_w"], d["ln1_b"], spec.eps)
         qkv = _bf16((M, 3 * H), dev)
         L.gemm(h1, sh.wqkv, qkv, M=M, N=3 * H, K=H, bias=sh.bqkv)
-        o, lse = _attention_fwd(spec, qkv, B, S, mask2d)
         rb = c = None
         if spec.mask_mode == "rank1":
             # P + m  =>  ctx += sum_k m[b,k] V[b,k,:]  (same vector for every query); keep it fp32 end to end
-            c = _f32((B, H), dev)
-            L.masked_colsum(qkv[:, 2 * H:], mask2d, c, B=B, S=S, N=H, ld=3 * H)
-            rb = _f32((B, H), dev)
-            L.call("tavk_small_linear_fwd", c.data_ptr(), d["wo"].data_ptr(), None, rb.data_ptr(), B, H, H)
+            c, rb = _f32((B, H), dev), _f32((B, H), dev)
+            with _SideWork(dev) as sw:      # next to the attention forward
+                L.masked_colsum(qkv[:, 2 * H:], mask2d, c, B=B, S=S, N=H, ld=3 * H)
+                L.call("tavk_small_linear_fwd", c.data_ptr(), d["wo"].data_ptr(), None, rb.data_ptr(), B, H, H)
+            o, lse = _attention_fwd(spec, qkv, B, S, mask2d)
+            sw.join()
+        else:
+            o, lse = _attention_fwd(spec, qkv, B, S, mask2d)
         x1 = _f32((M, H), dev)
         L.gemm(o, sh.wo, x1, M=M, N=H, K=H, bias=d["bo"], resid=x, rowbias=rb, rows_per_group=S)
         h2, _, mean2, rstd2 = L.layernorm_fwd(x1, d["ln2_w"], d["ln2_b"], spec.eps)
@@ -380,16 +424,19 @@ def _layer_bwd(spec, p, sh, sv, dy, dy_bf, B, S, mask2d, need_dx_bf, b2_done=Fal
         # LayerNorm backward also emits the column sums of dx1 (= out-projection bias gradient)
         dx1, dx1_bf = L.layernorm_bwd(dh2, sv.x1, sv.mean2, sv.rstd2, d["ln2_w"], go.target("ln2_w"), go.target("ln2_b"),
                                       resid=dy, want_f32=True, want_bf16=True, dx_colsum=go.target("bo"))
-        wo_t = _wgrad(dx1_bf, sv.o, H, H, M, out=go.target("wo"))
-        dc = None
+        dc = sw = None
+        wo_t = go.target("wo")
         if spec.mask_mode == "rank1":
-            drb = _f32((B, H), dev)
-            L.masked_colsum(dx1, None, drb, B=B, S=S, N=H, ld=H)
-            dc = _f32((B, H), dev)
-            L.call("tavk_small_linear_bwd_x", drb.data_ptr(), d["wo"].data_ptr(), dc.data_ptr(), B, H, H, 0)
-            L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), wo_t.data_ptr(), None, B, H, H)
+            drb, dc = _f32((B, H), dev), _f32((B, H), dev)
+            with _SideWork(dev) as sw:      # next to the out-projection wgrad / dgrad GEMMs (dW_o: atomic adds on both sides)
+                L.masked_colsum(dx1, None, drb, B=B, S=S, N=H, ld=H)
+                L.call("tavk_small_linear_bwd_x", drb.data_ptr(), d["wo"].data_ptr(), dc.data_ptr(), B, H, H, 0)
+                L.call("tavk_small_linear_bwd_w", drb.data_ptr(), sv.c.data_ptr(), wo_t.data_ptr(), None, B, H, H)
+        _wgrad(dx1_bf, sv.o, H, H, M, out=wo_t)
         do = _bf16((M, H), dev)
         L.gemm(dx1_bf, sh.wo, do, M=M, N=H, K=H, b_mn=True)
+        if sw is not None:
+            sw.join()
         dqkv = _attention_bwd(spec, sv, do, B, S, mask2d, dc, go)
         _qkv_grads(go, dqkv, sv.h1, H, M)
         dh1 = _f32((M, H), dev)

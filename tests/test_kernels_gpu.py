@@ -31,7 +31,8 @@ def gen(seed=0):
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (300, 768, 768), (5168, 2304, 768), (1000, 3072, 776), (16, 768, 1024)])
 @pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_operand_majors(L, a_mn, b_mn, shape, block_n):
+@pytest.mark.parametrize("cta_pair", [1, 2])       # single-CTA tiles | CTA pairs (cta_group::2) wherever M > 128
+def test_gemm_operand_majors(L, a_mn, b_mn, shape, block_n, cta_pair):
     M, N, K = shape
     if (a_mn and M % 8) or (b_mn and N % 8):
         pytest.skip("MN-major operand needs a row count that is a multiple of 8")
@@ -41,13 +42,16 @@ def test_gemm_operand_majors(L, a_mn, b_mn, shape, block_n):
     ref = A.float() @ B.float().t()
     out = torch.full((M, N), float("nan"), device="cuda")
     L.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, out, M=M, N=N, K=K, a_mn=a_mn,
-           b_mn=b_mn, block_n=block_n)
+           b_mn=b_mn, block_n=block_n, cta_pair=cta_pair)
     # fp32 accumulation of exact bf16 products: only summation-order noise is allowed
     assert rel_l2(out, ref) < 1e-5
     assert (out - ref).abs().max().item() < 1e-3 * math.sqrt(K)
 
 
-def test_gemm_epilogues(L):
+@pytest.mark.parametrize("cta_pair", [1, 2])
+def test_gemm_epilogues(L, cta_pair, monkeypatch):
+    _gemm = L.gemm
+    monkeypatch.setattr(L, "gemm", lambda *a, **k: _gemm(*a, cta_pair=cta_pair, **k))
     g = gen(2)
     M, N, K, S = 646, 768, 768, 323
     A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
@@ -408,11 +412,15 @@ def test_masked_mean_pool_lengths(L):
     assert (engine.mean_pool(x.detach()) - x.detach().mean(dim=1)).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("cta_pair", [1, 2])
 @pytest.mark.parametrize("M,N,K", [(300, 136, 200), (129, 72, 64), (5168, 768, 768)])
-def test_gemm_tma_store_epilogue_edges(L, M, N, K):
+def test_gemm_tma_store_epilogue_edges(L, M, N, K, cta_pair, monkeypatch):
     """bf16 outputs leave through TMA stores (csrc/gemm_tcgen05.cu epilogue_loop_tma): ragged M / N edges are clipped by
     the TMA unit, bias arrives as broadcast loads, the GELU' multiplier as TMA-loaded boxes; checked against torch and
-    against the coalesced-store epilogue (TAVK_GEMM_TMA_EPI=0 is read once per process, so the reference here is torch)."""
+    against the coalesced-store epilogue (TAVK_GEMM_TMA_EPI=0 is read once per process, so the reference here is torch).
+    cta_pair = 2: the same through CTA pairs, whose lower CTA may own rows past M."""
+    _gemm = L.gemm
+    monkeypatch.setattr(L, "gemm", lambda *a, **k: _gemm(*a, cta_pair=cta_pair, **k))
     g = gen(31)
     A = (torch.randn(M, K, generator=g) * 0.5).cuda().bfloat16()
     W = (torch.randn(N, K, generator=g) * 0.1).cuda().bfloat16()
