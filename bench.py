@@ -320,14 +320,16 @@ def main():
             os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
         except (AttributeError, OSError):
             pass
-        # Optional (TAVK_COMM_SMS=n): give NCCL a fixed CTA budget and keep as many SMs out of the persistent GEMM's grid
-        # (tavk_reserve_sms).  Off by default: measured at 2 GPUs it costs more than it hides (649 vs 676 samples/s, n=8).
+        # Optional (TAVK_COMM_SMS=n): give NCCL a fixed CTA budget and keep as many SMs out of the persistent GEMM's grid,
+        # either for every GEMM (TAVK_COMM_SMS_SCOPE=all: measured at 2 GPUs it costs more than it hides, 649 vs 676
+        # samples/s with n=8) or only while backward runs and gradient all-reduces are in flight (default scope).
         comm_sms = int(os.environ.get("TAVK_COMM_SMS", "0"))
+        comm_scope = os.environ.get("TAVK_COMM_SMS_SCOPE", "backward")
         if comm_sms > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
             os.environ.setdefault("NCCL_MIN_CTAS", str(min(4, comm_sms)))
         dist.init_process_group("nccl", device_id=dev)
-        if comm_sms > 0:
+        if comm_sms > 0 and comm_scope == "all":
             L.reserve_sms(comm_sms)
     L.require_device()   # fails loudly when the CUDA extension / an sm_100 device is missing: no fallback
     if args.no_fusion_128:
@@ -360,7 +362,8 @@ def main():
     params = [p for p in model.parameters() if p.requires_grad] + [p for p in pre.parameters() if p.requires_grad]
     opt = FusedAdamW(params, lr=1e-5, weight_decay=1e-4)
     runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=args.bucket_mb, use_cuda_graph=not args.no_graph,
-                                grad_reduce_dtype=torch.bfloat16 if args.grad_reduce == "bf16" else None)
+                                grad_reduce_dtype=torch.bfloat16 if args.grad_reduce == "bf16" else None,
+                                comm_sms=int(os.environ.get("TAVK_COMM_SMS", "0")) if (world > 1 and os.environ.get("TAVK_COMM_SMS_SCOPE", "backward") == "backward") else 0)
 
     host_inputs, host_labels = syn.make_batch(cfg, seed=1234 + rank, B=B)
     host_inputs = [{k: v.pin_memory() for k, v in d.items()} for d in host_inputs]

@@ -913,7 +913,9 @@ extern "C" int tavk_gemm_bf16(const tavk_gemm_args* a, void* stream_) {
     int block_n = 256;
     if (a->block_n == 64 || a->block_n == 128 || a->block_n == 256) block_n = a->block_n;
     else if (a->N <= 64) block_n = 64;
-    else if (a->N <= 128 || waves_eff(128) > waves_eff(256) * 1.15) block_n = 128;
+    // (a 128-wide tile runs at ~0.8x the rate of a 256-wide one — twice the A traffic per FLOP — so it has to win more than
+    // that in wave quantisation: M = 5168, N = 2304 measured 24.0 us with 128-wide tiles, 20.9 us with 256-wide ones)
+    else if (a->N <= 128 || waves_eff(128) > waves_eff(256) * 1.3) block_n = 128;
     // CTA pairs (cta_group::2, 256-row tiles): plain ungrouped problems with at least two row blocks.  The CTA count and
     // its wave quantisation are those of the single-CTA tiling (a pair = two CTAs = two 128-row blocks), except for the
     // idle lower half of the last pair when the number of row blocks is odd.  a->cta_pair: 0 heuristic, 1 never, 2 force.

@@ -335,6 +335,121 @@ small_linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict_
     if (db && k == 0) atomicAdd(db + n, sb);
 }
 
+
+// ---------------------------------------------------------------- tiled fp32 GEMM for the aligned small linears
+// C[M,N] (=|+=) sum_k A(m,k) B(k,n) (+ bias[n]) with A(m,k) = TA ? a[k*lda + m] : a[m*lda + k] and
+// B(k,n) = TB ? b[n*ldb + k] : b[k*ldb + n]; everything a multiple of 4 and 16-byte aligned.  The three small linears of
+// the fusion attention's rank-1 path ([B,768] x [768,768], forward / dgrad / wgrad) are 19-150 MFLOP each; the
+// warp-per-output kernels above take 6-35 us for them because every warp walks K serially behind global-memory latency.
+// Here a 256-thread block owns a 32 x 64 tile of C and one K-slice (blockIdx.z): operands pass through shared memory
+// with 16-byte global loads, 2 x 4 outputs per thread, and enough (tile, K-slice) blocks to cover the SMs about twice;
+// K-slices combine with red.global.add into a zeroed (or accumulating) C.  rowsum (TA only, blockIdx.x == 0):
+// rowsum[m] += sum_k A(m,k) — the bias gradient that rides on the weight-gradient form.
+constexpr int kSgBM = 32, kSgBN = 64, kSgBK = 32;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+small_gemm_f32_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, float* __restrict__ c, int ldc,
+                      const float* __restrict__ bias, float* __restrict__ rowsum, int M, int N, int K, int k_per_split,
+                      int atomic) {
+    pdl_wait();   // programmatic dependent launch: see common.cuh
+    __shared__ __align__(16) float As[kSgBK][kSgBM + 4];
+    __shared__ __align__(16) float Bs[kSgBK][kSgBN + 4];
+    const int t = threadIdx.x;
+    const int n0 = blockIdx.x * kSgBN, m0 = blockIdx.y * kSgBM;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    const int tx = t & 15, ty = t >> 4;          // 4 columns (tx*4 ..) x 2 rows (ty*2 ..) per thread
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float rs = 0.f;
+    for (int k0 = k_begin; k0 < k_end; k0 += kSgBK) {
+        // ---- A tile -> As[k][m]
+        {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (TA) {                                   // contiguous along m: thread = (k = t/8, 4 m)
+                const int k = k0 + (t >> 3), m = m0 + (t & 7) * 4;
+                if (k < k_end && m < M) v = __ldg(reinterpret_cast<const float4*>(a + (size_t)k * lda + m));
+                *reinterpret_cast<float4*>(&As[t >> 3][(t & 7) * 4]) = v;
+            } else {                                    // contiguous along k: thread = (m = t/8, 4 k), stored transposed
+                const int m = m0 + (t >> 3), k = k0 + (t & 7) * 4;
+                if (m < M && k < k_end) v = __ldg(reinterpret_cast<const float4*>(a + (size_t)m * lda + k));
+                const int kk = (t & 7) * 4, mm = t >> 3;
+                As[kk][mm] = v.x; As[kk + 1][mm] = v.y; As[kk + 2][mm] = v.z; As[kk + 3][mm] = v.w;
+            }
+        }
+        // ---- B tile -> Bs[k][n]  (2048 elements: two float4 per thread)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (TB) {                                   // contiguous along k: thread = (n = t/8 + 32h, 4 k), stored transposed
+                const int nn = (t >> 3) + 32 * h, kk = (t & 7) * 4;
+                if (n0 + nn < N && k0 + kk < k_end) v = __ldg(reinterpret_cast<const float4*>(b + (size_t)(n0 + nn) * ldb + k0 + kk));
+                Bs[kk][nn] = v.x; Bs[kk + 1][nn] = v.y; Bs[kk + 2][nn] = v.z; Bs[kk + 3][nn] = v.w;
+            } else {                                    // contiguous along n: thread = (k = t/16 + 16h, 4 n)
+                const int kk = (t >> 4) + 16 * h, nn = (t & 15) * 4;
+                if (k0 + kk < k_end && n0 + nn < N) v = __ldg(reinterpret_cast<const float4*>(b + (size_t)(k0 + kk) * ldb + n0 + nn));
+                *reinterpret_cast<float4*>(&Bs[kk][nn]) = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSgBK; ++k) {
+            const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            acc[0][0] += a0 * b4.x; acc[0][1] += a0 * b4.y; acc[0][2] += a0 * b4.z; acc[0][3] += a0 * b4.w;
+            acc[1][0] += a1 * b4.x; acc[1][1] += a1 * b4.y; acc[1][2] += a1 * b4.z; acc[1][3] += a1 * b4.w;
+        }
+        if (rowsum != nullptr && blockIdx.x == 0 && t < kSgBM) {
+#pragma unroll
+            for (int k = 0; k < kSgBK; ++k) rs += As[k][t];
+        }
+        __syncthreads();
+    }
+    if (rowsum != nullptr && blockIdx.x == 0 && t < kSgBM && m0 + t < M) atomicAdd(rowsum + m0 + t, rs);
+    const int n = n0 + tx * 4;
+    if (n >= N) return;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr && blockIdx.z == 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= M) continue;
+        float* o = c + (size_t)m * ldc + n;
+        const float v0 = acc[i][0] + b4.x, v1 = acc[i][1] + b4.y, v2 = acc[i][2] + b4.z, v3 = acc[i][3] + b4.w;
+        if (atomic) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+        else *reinterpret_cast<float4*>(o) = make_float4(v0, v1, v2, v3);
+    }
+}
+
+static bool small_gemm_ok(const void* p0, const void* p1, const void* p2, const void* p3, int M, int N, int K) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(p2) |
+                           reinterpret_cast<uintptr_t>(p3);
+    // worth it from a few MFLOP up (the classifier head and other slivers stay on the warp-per-output kernels)
+    return (bits & 15) == 0 && (M & 3) == 0 && (N & 3) == 0 && (K & 3) == 0 && (long long)M * N * K >= (1ll << 21) && N >= 64;
+}
+
+// C (=|+=) A B as described above.  `overwrite`: C is replaced (zeroed first when K is split), else accumulated into.
+template <bool TA, bool TB>
+static int launch_small_gemm(const float* a, int lda, const float* b, int ldb, float* c, int ldc, const float* bias, float* rowsum,
+                             int M, int N, int K, bool overwrite, cudaStream_t stream) {
+    const int gx = (N + kSgBN - 1) / kSgBN, gy = (M + kSgBM - 1) / kSgBM;
+    const int kb = (K + kSgBK - 1) / kSgBK;
+    int splits = (2 * sm_count() + gx * gy - 1) / (gx * gy);
+    if (splits > kb) splits = kb;
+    if (splits < 1) splits = 1;
+    const int k_per_split = ((kb + splits - 1) / splits) * kSgBK;
+    splits = (K + k_per_split - 1) / k_per_split;
+    TAVK_CHECK(gy <= 65535 && splits <= 65535, 2, "small gemm: shape too large for this kernel (M=%d K=%d)", M, K);
+    const int atomic = (!overwrite || splits > 1) ? 1 : 0;
+    if (overwrite && splits > 1) TAVK_CUDA(cudaMemsetAsync(c, 0, (size_t)M * ldc * sizeof(float), stream));
+    TAVK_CUDA(launch_kernel(small_gemm_f32_kernel<TA, TB>, dim3(gx, gy, splits), dim3(256), (size_t)(0), stream, a, lda, b, ldb,
+                            c, ldc, bias, rowsum, M, N, K, k_per_split, atomic));
+    TAVK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------- casts / scaling / dropout
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
     pdl_wait();   // programmatic dependent launch: see common.cuh
@@ -551,6 +666,8 @@ extern "C" int tavk_small_linear_fwd(const float* x, const float* w, const float
     TAVK_CHECK((K & 3) != 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, 1,
                "tavk_small_linear_fwd: x and w must be 16-byte aligned when K %% 4 == 0");
     if (M <= 0 || N <= 0) return 0;
+    if (small_gemm_ok(x, w, y, b, M, N, K))           // y = x w^T + b as a tiled GEMM (A = x, B(k,n) = w[n,k])
+        return launch_small_gemm<false, true>(x, K, w, K, y, N, b, nullptr, M, N, K, true, STREAM(stream));
     const int gx = (N + 7) / 8;                       // 8 warps (output columns) per block
     const int gy = (M + kSlRows - 1) / kSlRows;
     TAVK_CHECK(gy <= 65535, 2, "tavk_small_linear_fwd: M=%d too large for this kernel", M);
@@ -563,6 +680,8 @@ extern "C" int tavk_small_linear_bwd_x(const float* dy, const float* w, float* d
                                        void* stream) {
     TAVK_CHECK(dy && w && dx, 1, "tavk_small_linear_bwd_x: null pointer");
     if (M <= 0 || K <= 0) return 0;
+    if (N > 0 && small_gemm_ok(dy, w, dx, nullptr, M, K, N))   // dx[M,K] (+)= dy[M,N] w[N,K]
+        return launch_small_gemm<false, false>(dy, N, w, K, dx, K, nullptr, nullptr, M, K, N, !accumulate, STREAM(stream));
     const long long total = (long long)M * K;
     if (!accumulate) TAVK_CUDA(cudaMemsetAsync(dx, 0, (size_t)total * sizeof(float), STREAM(stream)));
     if (N <= 0) return 0;
@@ -580,6 +699,8 @@ extern "C" int tavk_small_linear_bwd_w(const float* dy, const float* x, float* d
     TAVK_CHECK((K & 3) != 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0, 1,
                "tavk_small_linear_bwd_w: x and dw must be 16-byte aligned when K %% 4 == 0");
     if (N <= 0 || K <= 0) return 0;
+    if (dw != nullptr && M > 0 && small_gemm_ok(dy, x, dw, nullptr, N, K, M))    // dw[N,K] += dy^T[N,M] x[M,K]; db[N] += row sums of dy^T
+        return launch_small_gemm<true, false>(dy, N, x, K, dw, K, nullptr, db, N, K, M, false, STREAM(stream));
     const long long total = (long long)N * ((K & 3) == 0 ? K / 4 : K);
     TAVK_CUDA(launch_kernel(small_linear_bwd_w_kernel, dim3((int)((total + 127) / 128)), dim3(128), (size_t)(0), STREAM(stream), dy, x, dw, db, M, N, K));
     TAVK_CUDA(cudaGetLastError());

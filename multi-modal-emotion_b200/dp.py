@@ -56,6 +56,7 @@ class GradBuckets:
             i = j - 1
         del ends
         self.pending = [0] * len(self.buckets)
+        self.reported = set()
         self.streams = [set() for _ in self.buckets]
         self.works = []
         self.enabled = False
@@ -69,12 +70,13 @@ class GradBuckets:
         from . import engine
 
         self.pending = [n for (_, _, n) in self.buckets]
+        self.reported = set()                           # parameters already counted in this backward pass (see _hook)
         self.streams = [set() for _ in self.buckets]    # streams that wrote gradients of each bucket (tav.branch_streams)
         self.works = []
         self.enabled = True
         self.launched = 0
-        # parameters whose gradient the layer engine accumulates straight into the flat buffer never reach autograd's
-        # AccumulateGrad (and so never fire the hooks above): the engine reports them layer by layer instead
+        # parameters whose gradient the layer engine accumulates straight into the flat buffer are reported by the engine
+        # layer by layer (autograd only sees a None gradient for them, after the whole stack's backward has returned)
         engine.grad_written_hook = self._written
 
     def _written(self, params):
@@ -102,8 +104,15 @@ class GradBuckets:
         self.launched += 1
 
     def _hook(self, p):
-        if not self.enabled:
+        """A parameter's gradient for this backward pass is complete (its kernels are enqueued on the current stream).
+        Counted ONCE per pass: a parameter handled by the engine's gradient sink is reported by the engine when its layer
+        is done and then again by autograd — torch >= 2.x fires the post-accumulate-grad hook even for the None gradient
+        the stack's backward returns for it (it did not when this was first written).  Counting both let a bucket that
+        mixes such parameters with ones written later (another branch stream) reach zero early: it was all-reduced
+        before those gradients existed and they stayed rank-local (tests/test_dp_nccl_gpu.py, tests/test_dp_cpu.py)."""
+        if not self.enabled or id(p) in self.reported:
             return
+        self.reported.add(id(p))
         b = self.param_bucket[id(p)]
         if self.cuda:
             self.streams[b].add(torch.cuda.current_stream())
@@ -138,13 +147,17 @@ class DataParallelTAV:
     normalisation, backward overlapped with bucketed gradient all-reduce, fused clip + AdamW on identical gradients."""
 
     def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=128, group=None,
-                 use_cuda_graph=False, graph_warmup=3, scheduler=None, grad_reduce_dtype=None):
+                 use_cuda_graph=False, graph_warmup=3, scheduler=None, grad_reduce_dtype=None, comm_sms=0):
         """``scheduler``: the reference's CosineAnnealingWarmRestarts (or any torch scheduler over ``optimizer``).
         ``train_step(..., sched_t=epoch + i/iters)`` steps it after the update exactly like the reference loop
         (train_model/tav_train.py:63); its learning rate reaches the captured graph through a device scalar."""
         self.model, self.pre, self.criterion, self.opt = model, PREFormer, criterion, optimizer
         self.scheduler = scheduler
         self.grad_reduce_dtype = grad_reduce_dtype
+        # comm_sms > 0 (N > 1): while backward runs — the only time gradient all-reduces are in flight — every persistent
+        # GEMM leaves that many SMs out of its grid (tavk_gemm_args.max_ctas), so its CTAs never queue behind the
+        # collective kernels that hold those SMs; forward GEMMs keep the whole machine.  Pair it with NCCL_MAX_CTAS.
+        self.comm_sms = int(comm_sms)
         self.clip, self.group, self.bucket_bytes = clip, group, bucket_mb << 20
         self.buckets = None
         self.use_cuda_graph, self.graph_warmup = use_cuda_graph, graph_warmup
@@ -335,7 +348,17 @@ class DataParallelTAV:
         if self.buckets is not None:
             self.buckets.start_backward()
         loss = get_statistics(inputs, labels, self.model, self.pre, parts_criterion, Metric, check=check, epoch=epoch)
-        loss.backward()
+        if self.world > 1 and self.comm_sms > 0 and self.buckets is not None:
+            from . import _lib as L
+
+            keep = L.gemm_reserved_sms
+            L.gemm_reserved_sms = self.comm_sms
+            try:
+                loss.backward()
+            finally:
+                L.gemm_reserved_sms = keep
+        else:
+            loss.backward()
         if self.world > 1:
             if self.buckets is not None:
                 self.buckets.finish()

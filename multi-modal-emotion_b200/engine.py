@@ -153,9 +153,10 @@ def _wgrad(dy_bf, x_bf, rows_out, cols_out, tokens, out=None, lda=None):
 # Gradient sink: when a parameter already owns a contiguous fp32 ``.grad`` (optim.FlatParams points every .grad at a
 # slice of one flat buffer, zeroed by the fused AdamW kernel), the stack's backward accumulates straight into it — the
 # wgrad GEMMs' red.global.add epilogue, the LayerNorm / column-sum atomics — and returns None for that input, instead
-# of materialising a temporary and letting autograd launch one add_ per parameter.  Because autograd's
-# post-accumulate-grad hooks do not fire for such parameters, ``grad_written_hook(params)`` is called after each
-# layer's kernels are enqueued (dp.GradBuckets uses it to launch bucket all-reduces during backward).
+# of materialising a temporary and letting autograd launch one add_ per parameter.  ``grad_written_hook(params)`` is
+# called after each layer's kernels are enqueued (dp.GradBuckets uses it to launch bucket all-reduces during backward,
+# layer by layer, instead of when autograd gets to the stack's parameters after the whole stack has run; autograd's own
+# post-accumulate-grad hooks fire for these parameters too, with the None gradient — GradBuckets counts each once).
 grad_sink_enabled = True
 grad_written_hook = None
 
@@ -204,6 +205,9 @@ def _attention_fwd(spec, qkv, B, S, key_bias):
 # stream is joined back before the calling stream touches or frees them, so the caching allocator needs no record_stream.
 rank1_side_stream = os.environ.get("TAVK_RANK1_SIDE", "1") != "0"
 _RANK1_STREAMS = {}
+# (Running the weight-gradient GEMMs on a second stream beside the dgrad chain was tried the same way and lost: two
+# persistent one-CTA-per-SM GEMMs cannot share an SM, so they only interleave at CTA granularity — fusion block 5.67 ms
+# against 5.64 ms, the full step 396 against 407 samples/s.)
 
 
 class _SideWork:
@@ -218,8 +222,10 @@ class _SideWork:
             if self.side is None:
                 self.side = _RANK1_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=-1)
         self._ctx = None
+        self.used = False
 
     def __enter__(self):
+        self.used = True
         if self.side is not None:
             self.side.wait_stream(self.main)
             self._ctx = torch.cuda.stream(self.side)
@@ -233,8 +239,9 @@ class _SideWork:
         return False
 
     def join(self):
-        if self.side is not None:
+        if self.side is not None and self.used:
             self.main.wait_stream(self.side)
+            self.used = False
 
 
 debug_dropout_masks = None   # tests set this to a list: every keep-mask drawn by the layer engine is appended (uint8)

@@ -111,3 +111,50 @@ def test_bucket_layout_covers_flat_buffer_once():
         assert e0 == s1
     assert sum(n for _, _, n in b.buckets) == len(flat.params)
     b.remove()
+
+
+class _SinkLinear(torch.autograd.Function):
+    """A layer that, like the engine's gradient sink, accumulates its weight gradient straight into ``w.grad`` and hands
+    autograd None for it, then reports the parameter through ``engine.grad_written_hook``."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from multi_modal_emotion_b200 import engine
+
+        x, w = ctx.saved_tensors
+        w.grad.add_(dy.t() @ x)
+        if engine.grad_written_hook is not None:
+            engine.grad_written_hook([w])
+        return dy @ w, None
+
+
+def test_sink_parameter_is_counted_once_per_backward():
+    """Regression (found by tests/test_dp_nccl_gpu.py on two B200s): torch fires a parameter's post-accumulate-grad hook
+    even when the backward returned None for it, so a sink parameter was reported twice — by the engine and by autograd —
+    and a bucket it shared with a parameter whose gradient arrives later was all-reduced before that gradient existed."""
+    from multi_modal_emotion_b200 import dp
+    from multi_modal_emotion_b200.optim import FlatParams
+
+    torch.manual_seed(0)
+    first = torch.nn.Parameter(torch.randn(6, 5))     # used first in forward -> its gradient arrives LAST in backward
+    sink = torch.nn.Parameter(torch.randn(4, 6))      # gradient written early, by the sink
+    flat = _cpu_flat(FlatParams, [first, sink])
+    launches = []
+
+    class Probe(dp.GradBuckets):
+        def _launch(self, b):
+            launches.append((b, first.grad.abs().sum().item() > 0, sink.grad.abs().sum().item() > 0))
+            self.launched += 1
+
+    buckets = Probe(flat, bucket_bytes=1 << 20, group=None)     # one bucket holds both
+    assert len(buckets.buckets) == 1
+    buckets.start_backward()
+    x = torch.randn(3, 5)
+    _SinkLinear.apply(torch.nn.functional.linear(x, first), sink).sum().backward()
+    buckets.finish()
+    assert launches == [(0, True, True)]      # launched once, after BOTH gradients had been written

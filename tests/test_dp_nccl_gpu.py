@@ -102,6 +102,9 @@ def test_two_nccl_ranks_reproduce_the_single_process_step(tmp_path):
         errs = [((got[k] - g).norm().item() / g.norm().item(), k) for k, g in r["ref"].items() if g.norm().item() > 1e-6 * gmax]
         worst = max(errs)
         print("step %d: whole-model flat gradient rel-L2 %.2e; worst tensor %.2e (%s)" % (i + 1, (num / den) ** 0.5, worst[0], worst[1]))
+        big = sorted(((got[k] - g).norm().item(), k) for k, g in r["ref"].items())[-8:]
+        for ae, k in reversed(big):     # where the flat error comes from: absolute error, the tensor's norm, its share of the total
+            print("    |err| %.3e  |g| %.3e  share of flat err^2 %.2f  %s" % (ae, r["ref"][k].norm().item(), ae * ae / max(num, 1e-30), k))
         assert (num / den) ** 0.5 < 2e-2
         for e, k in errs:
             if k.endswith("key.bias") or k.endswith("k_proj.bias"):
