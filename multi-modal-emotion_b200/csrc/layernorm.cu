@@ -3,6 +3,8 @@
 // models/tav.py:439,443,445,447, plus the LayerNorms inside the HF RoBERTa / Wav2Vec2 / VideoMAE layers.
 // Statistics are fp32 and two-pass (mean, then centred variance) because the reference's post-softmax mask quirk
 // drives the residual stream to 1e6..4e7 where E[x^2]-mu^2 cancels catastrophically.
+#include <stdlib.h>
+
 #include "../../include/tavk.h"
 #include "common.cuh"
 
@@ -95,11 +97,16 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         const float mu = mean[row], rs = rstd[row];
         const float4* dyr = reinterpret_cast<const float4*>(dy + (size_t)row * H);
         const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * H);
-        float4 d[VEC], xh[VEC];
+        float4 d[VEC], xh[VEC], rr[VEC];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
+        for (int i = 0; i < VEC; ++i) d[i] = dyr[lane + 32 * i];
+        if (dx_resid) {     // requested with dy and x: one more operand row in flight per warp instead of a second round trip
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) rr[i] = reinterpret_cast<const float4*>(dx_resid + (size_t)row * H)[lane + 32 * i];
+        }
+#pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            d[i] = dyr[lane + 32 * i];
             const float4 xv = xr[lane + 32 * i];
             xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs;
             xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
@@ -120,10 +127,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             o.y = rs * (d[i].y - c2 - xh[i].y * c1);
             o.z = rs * (d[i].z - c2 - xh[i].z * c1);
             o.w = rs * (d[i].w - c2 - xh[i].w * c1);
-            if (dx_resid) {
-                const float4 r = reinterpret_cast<const float4*>(dx_resid + (size_t)row * H)[lane + 32 * i];
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
+            if (dx_resid) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
             dc[i].x += o.x; dc[i].y += o.y; dc[i].z += o.z; dc[i].w += o.w;
             if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * H)[lane + 32 * i] = o;
             if (dx_bf16) {
@@ -190,7 +194,11 @@ extern "C" int tavk_layernorm_bwd(const float* dy, const float* x, const float* 
     if (M == 0) return 0;
     const int warps = 8;
     int grid = (M + warps - 1) / warps;
-    const int cap = sm_count() * 4;
+    // one RESIDENT wave: the kernel keeps ~180 registers per thread (three column accumulators), so one 256-thread block fits
+    // per SM; blocks beyond that only queue behind it and each pays the gamma prologue and three block-reduction passes
+    // (TAVK_LN_BWD_WAVES: measurement knob, blocks per SM)
+    static const int waves = getenv("TAVK_LN_BWD_WAVES") ? atoi(getenv("TAVK_LN_BWD_WAVES")) : 1;
+    const int cap = sm_count() * (waves > 0 ? waves : 1);
     if (grid > cap) grid = cap;
     const size_t smem = (size_t)warps * H * sizeof(float);
     __nv_bfloat16* db16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
