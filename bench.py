@@ -363,6 +363,7 @@ def main():
     opt = FusedAdamW(params, lr=1e-5, weight_decay=1e-4)
     runner = dp.DataParallelTAV(model, pre, crit, opt, clip=1.0, bucket_mb=args.bucket_mb, use_cuda_graph=not args.no_graph,
                                 grad_reduce_dtype=torch.bfloat16 if args.grad_reduce == "bf16" else None,
+                                row_sparse=os.environ.get("TAVK_ROW_SPARSE", "1") != "0",
                                 comm_sms=int(os.environ.get("TAVK_COMM_SMS", "0")) if (world > 1 and os.environ.get("TAVK_COMM_SMS_SCOPE", "backward") == "backward") else 0)
 
     host_inputs, host_labels = syn.make_batch(cfg, seed=1234 + rank, B=B)

@@ -28,33 +28,67 @@ def global_loss(num, den, group=None):
     return num / den_g, num_g / den_g
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _scatter_rows(grad, idx, dy, skip_idx):
+    """grad[idx[r], :] += dy[r, :] (rows with idx == skip_idx or outside the table are dropped): the embedding-backward
+    kernel on the GPU; index_add_ for the CPU (gloo) tests of the plumbing."""
+    if grad.is_cuda:
+        from . import _lib as L
+
+        L.call("tavk_embedding_scatter_add", dy.data_ptr(), idx.data_ptr(), grad.data_ptr(), idx.numel(), dy.shape[-1],
+               grad.shape[0], -1 if skip_idx is None else int(skip_idx))
+        return
+    keep = (idx >= 0) & (idx < grad.shape[0])
+    if skip_idx is not None and skip_idx >= 0:
+        keep &= idx != skip_idx
+    grad.index_add_(0, idx[keep], dy[keep])
+
+
 class GradBuckets:
     """Splits a flat gradient buffer into parameter-aligned buckets and all-reduces each one as soon as every
     parameter in it has accumulated its gradient."""
 
-    def __init__(self, flat, bucket_bytes=32 << 20, group=None, reduce_dtype=None):
+    def __init__(self, flat, bucket_bytes=32 << 20, group=None, reduce_dtype=None, row_sparse=()):
         """``reduce_dtype=torch.bfloat16``: opt-in gradient compression — each bucket is cast to bf16 on the communication
         stream, summed by NCCL in bf16 and cast back (half the NVLink bytes and half the time the collective kernels hold
-        SMs; the summed gradient carries bf16 rounding, 2^-9 relative).  Default: exact fp32 sums."""
+        SMs; the summed gradient carries bf16 rounding, 2^-9 relative).  Default: exact fp32 sums.
+
+        ``row_sparse``: embedding tables whose gradient has at most (tokens per rank) non-zero rows — RoBERTa's two
+        50265 x 768 word-embedding tables are 2 x 154 MB of the 1.58 GB gradient, produced last in backward, with 1120
+        non-zero rows each.  They are left out of the dense buckets; their producer hands (token ids, gradient rows) to
+        ``exchange_rows`` and every rank scatter-adds the other ranks' rows into its own table: 3.4 MB per rank on the
+        wire instead of a 154 MB all-reduce at the very end of backward, and the same sum."""
         self.flat, self.group = flat, group
         self.reduce_dtype = reduce_dtype
         self.buckets = []   # (start, end, n_params)
         self.param_bucket = {}
+        self.row_sparse = {id(p) for p in row_sparse}
         cap = max(1, bucket_bytes // 4)
-        # backward produces gradients roughly in reverse registration order: build buckets from the tail
-        ends = [o + p.numel() for p, o in zip(flat.params, flat.offsets)]
+        # backward produces gradients roughly in reverse registration order: build buckets from the tail; a bucket is a
+        # contiguous range of the flat buffer, so a row-sparse table closes the bucket on either side of it
         i = len(flat.params) - 1
         while i >= 0:
-            end = flat.numel if not self.buckets else self.buckets[-1][0]
+            if id(flat.params[i]) in self.row_sparse:
+                i -= 1
+                continue
+            end = flat.offsets[i] + (flat.params[i].numel() + 63) // 64 * 64
+            if i == len(flat.params) - 1:
+                end = flat.numel
             j = i
-            while j > 0 and end - flat.offsets[j - 1] <= cap:
+            while j > 0 and id(flat.params[j - 1]) not in self.row_sparse and end - flat.offsets[j - 1] <= cap:
                 j -= 1
             start = flat.offsets[j]
             self.buckets.append((start, end, i - j + 1))
             for k in range(j, i + 1):
                 self.param_bucket[id(flat.params[k])] = len(self.buckets) - 1
             i = j - 1
-        del ends
         self.pending = [0] * len(self.buckets)
         self.reported = set()
         self.streams = [set() for _ in self.buckets]
@@ -78,6 +112,34 @@ class GradBuckets:
         # parameters whose gradient the layer engine accumulates straight into the flat buffer are reported by the engine
         # layer by layer (autograd only sees a None gradient for them, after the whole stack's backward has returned)
         engine.grad_written_hook = self._written
+        engine.row_sparse_hook = self.exchange_rows if self.row_sparse else None
+
+    def exchange_rows(self, table, idx, dy, grad, skip_idx):
+        """Called by an embedding backward after it has scatter-added this rank's rows ``dy`` [rows, H] (token ids ``idx``)
+        into ``grad`` (the table's gradient): adds every other rank's rows too.  Returns False when ``table`` is not one
+        of the row-sparse tables (the caller's gradient then travels in a dense bucket)."""
+        if not self.enabled or id(table) not in self.row_sparse:
+            return False
+        world = dist.get_world_size(self.group)
+        rank = dist.get_rank(self.group)
+        rows, H = idx.numel(), dy.shape[-1]
+        idx, dy = idx.reshape(rows).contiguous(), dy.reshape(rows, H).contiguous()
+        cur = torch.cuda.current_stream() if self.cuda else None
+        if self.cuda:
+            self.comm_stream.wait_stream(cur)
+            idx.record_stream(self.comm_stream)
+            dy.record_stream(self.comm_stream)
+        ctx = torch.cuda.stream(self.comm_stream) if self.cuda else _NullCtx()
+        with ctx:
+            ids_all = torch.empty((world, rows), dtype=idx.dtype, device=idx.device)
+            dy_all = torch.empty((world, rows, H), dtype=dy.dtype, device=dy.device)
+            dist.all_gather([ids_all[r] for r in range(world)], idx, group=self.group)     # (views of one buffer: no copies)
+            dist.all_gather([dy_all[r] for r in range(world)], dy, group=self.group)
+            for r in range(world):
+                if r != rank:
+                    _scatter_rows(grad, ids_all[r], dy_all[r], skip_idx)
+        self.launched += 1
+        return True
 
     def _written(self, params):
         for p in params:
@@ -110,7 +172,7 @@ class GradBuckets:
         the stack's backward returns for it (it did not when this was first written).  Counting both let a bucket that
         mixes such parameters with ones written later (another branch stream) reach zero early: it was all-reduced
         before those gradients existed and they stayed rank-local (tests/test_dp_nccl_gpu.py, tests/test_dp_cpu.py)."""
-        if not self.enabled or id(p) in self.reported:
+        if not self.enabled or id(p) in self.reported or id(p) not in self.param_bucket:
             return
         self.reported.add(id(p))
         b = self.param_bucket[id(p)]
@@ -125,6 +187,7 @@ class GradBuckets:
         from . import engine
 
         engine.grad_written_hook = None
+        engine.row_sparse_hook = None
         if self.enabled:
             for b, n in enumerate(self.pending):
                 if n > 0:
@@ -147,7 +210,7 @@ class DataParallelTAV:
     normalisation, backward overlapped with bucketed gradient all-reduce, fused clip + AdamW on identical gradients."""
 
     def __init__(self, model, PREFormer, criterion, optimizer, clip=1.0, bucket_mb=128, group=None,
-                 use_cuda_graph=False, graph_warmup=3, scheduler=None, grad_reduce_dtype=None, comm_sms=0):
+                 use_cuda_graph=False, graph_warmup=3, scheduler=None, grad_reduce_dtype=None, comm_sms=0, row_sparse=True):
         """``scheduler``: the reference's CosineAnnealingWarmRestarts (or any torch scheduler over ``optimizer``).
         ``train_step(..., sched_t=epoch + i/iters)`` steps it after the update exactly like the reference loop
         (train_model/tav_train.py:63); its learning rate reaches the captured graph through a device scalar."""
@@ -158,6 +221,7 @@ class DataParallelTAV:
         # GEMM leaves that many SMs out of its grid (tavk_gemm_args.max_ctas), so its CTAs never queue behind the
         # collective kernels that hold those SMs; forward GEMMs keep the whole machine.  Pair it with NCCL_MAX_CTAS.
         self.comm_sms = int(comm_sms)
+        self.row_sparse = bool(row_sparse)      # exchange large embedding-table gradients as (ids, rows), see GradBuckets
         self.clip, self.group, self.bucket_bytes = clip, group, bucket_mb << 20
         self.buckets = None
         self.use_cuda_graph, self.graph_warmup = use_cuda_graph, graph_warmup
@@ -171,7 +235,9 @@ class DataParallelTAV:
             optimizer.on_materialize = self._on_materialize
 
     def _on_materialize(self, flat):
-        self.buckets = GradBuckets(flat, self.bucket_bytes, self.group, reduce_dtype=self.grad_reduce_dtype)
+        # embedding tables that announced themselves as row-sparse in the first (eager) step and are large enough to matter
+        sparse = [p for p in flat.params if self.row_sparse and getattr(p, "_tavk_row_sparse", False) and p.numel() >= (1 << 22)]
+        self.buckets = GradBuckets(flat, self.bucket_bytes, self.group, reduce_dtype=self.grad_reduce_dtype, row_sparse=sparse)
 
     # -- CUDA-graph path: the whole step (forward, loss, backward, bucketed all-reduce, clip + AdamW) is captured
     #    once per (shape, epoch-parity, check) and replayed; per step the host only enqueues the input copies and

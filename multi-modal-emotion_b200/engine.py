@@ -159,6 +159,10 @@ def _wgrad(dy_bf, x_bf, rows_out, cols_out, tokens, out=None, lda=None):
 # post-accumulate-grad hooks fire for these parameters too, with the None gradient — GradBuckets counts each once).
 grad_sink_enabled = True
 grad_written_hook = None
+# Row-sparse gradients: an embedding backward offers (table, token ids, gradient rows, the table's gradient, padding index)
+# after its own scatter-add; the data-parallel layer answers True when it adds the other ranks' rows itself
+# (dp.GradBuckets.exchange_rows) instead of all-reducing the dense table.
+row_sparse_hook = None
 
 
 def _sink(t):
@@ -697,6 +701,7 @@ class _RobertaEmbedFn(torch.autograd.Function):
         pos_ids = torch.empty((B, T), dtype=torch.int64, device=word.device)
         L.call("tavk_roberta_embed_fwd", ids.data_ptr(), word.data_ptr(), pos.data_ptr(), typ.data_ptr(), y.data_ptr(),
                pos_ids.data_ptr(), B, T, H, V, pos.shape[0], int(pad_id))
+        word._tavk_row_sparse = True      # its gradient has at most B*T non-zero rows (see row_sparse_hook)
         ctx.save_for_backward(ids, pos_ids)
         ctx.tables = (word, pos, typ)
         ctx.pads = pads
@@ -724,6 +729,8 @@ class _RobertaEmbedFn(torch.autograd.Function):
                 written.append(table)
             L.call("tavk_embedding_scatter_add", dy.data_ptr(), idx.data_ptr(), g.data_ptr(), B * T, H, table.shape[0],
                    -1 if skip is None else int(skip))
+            if table is word and row_sparse_hook is not None:
+                row_sparse_hook(table, idx, dy, g, skip)
         dtyp = None
         if ctx.needs_input_grad[3]:
             g = _sink(typ)

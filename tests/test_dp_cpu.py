@@ -158,3 +158,75 @@ def test_sink_parameter_is_counted_once_per_backward():
     _SinkLinear.apply(torch.nn.functional.linear(x, first), sink).sum().backward()
     buckets.finish()
     assert launches == [(0, True, True)]      # launched once, after BOTH gradients had been written
+
+
+class _SinkEmbedding(torch.autograd.Function):
+    """Embedding lookup whose backward does what engine._RobertaEmbedFn does: scatter-add this rank's rows into the table's
+    own .grad (gradient sink), offer (ids, rows) to ``engine.row_sparse_hook``, report the table as written."""
+
+    @staticmethod
+    def forward(ctx, ids, table):
+        ctx.save_for_backward(ids)
+        ctx.table = table
+        return table[ids]
+
+    @staticmethod
+    def backward(ctx, dy):
+        from multi_modal_emotion_b200 import engine
+
+        (ids,) = ctx.saved_tensors
+        t = ctx.table
+        t.grad.index_add_(0, ids.reshape(-1), dy.reshape(-1, dy.shape[-1]))
+        if engine.row_sparse_hook is not None:
+            engine.row_sparse_hook(t, ids, dy, t.grad, None)
+        if engine.grad_written_hook is not None:
+            engine.grad_written_hook([t])
+        return None, None
+
+
+def _sparse_toy():
+    torch.manual_seed(3)
+    return torch.nn.Embedding(50, 16), torch.nn.Linear(16, 7)
+
+
+def _sparse_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multi_modal_emotion_b200 import dp
+    from multi_modal_emotion_b200.optim import FlatParams
+
+    emb, head = _sparse_toy()
+    g = torch.Generator().manual_seed(11)
+    ids, y = torch.randint(0, 50, (8, 5), generator=g), torch.randint(0, 7, (8,), generator=g)
+    w = torch.rand(7, generator=g) + 0.5
+    params = [emb.weight] + list(head.parameters())
+    flat = _cpu_flat(FlatParams, params)
+    buckets = dp.GradBuckets(flat, bucket_bytes=1 << 20, group=None, row_sparse=[emb.weight])
+    assert id(emb.weight) not in buckets.param_bucket            # the table travels as rows, not in a dense bucket
+    assert sum(n for _, _, n in buckets.buckets) == len(params) - 1
+    buckets.start_backward()
+    sl = slice(rank * 4, (rank + 1) * 4)
+    num, den = _parts(head(_SinkEmbedding.apply(ids[sl], emb.weight).mean(1)), y[sl], w)
+    loss_bwd, _ = dp.global_loss(num, den)
+    loss_bwd.backward()
+    buckets.finish()
+    out[rank] = flat.grad.clone()
+    dist.destroy_process_group()
+
+
+def test_row_sparse_table_gradient_matches_dense_sum():
+    """The embedding table's gradient exchanged as (token ids, rows) between two ranks equals the single-process gradient
+    on the concatenated batch, like the dense buckets next to it."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sparse_worker, args=(world, port, out), nprocs=world, join=True)
+    emb, head = _sparse_toy()
+    g = torch.Generator().manual_seed(11)
+    ids, y = torch.randint(0, 50, (8, 5), generator=g), torch.randint(0, 7, (8,), generator=g)
+    w = torch.rand(7, generator=g) + 0.5
+    num, den = _parts(head(emb(ids).mean(1)), y, w)
+    (num / den).backward()
+    ref = torch.cat([torch.nn.functional.pad(p.grad.flatten(), (0, (-p.numel()) % 64)) for p in [emb.weight] + list(head.parameters())])
+    for r in range(world):
+        assert torch.allclose(out[r], ref, rtol=1e-5, atol=1e-7)

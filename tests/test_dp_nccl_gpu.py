@@ -74,6 +74,7 @@ def _worker(rank, world, port, tmp):
     opt.step = spy
     losses = [runner._eager_step(my_in, labels[shard], 1, "val").item() for _ in range(2)]
     assert runner.buckets is not None and runner.buckets.launched >= 2      # step 2 went through the bucketed path
+    assert len(runner.buckets.row_sparse) == 2      # ... with both RoBERTa word-embedding tables exchanged as (ids, rows)
     if rank == 0:
         model1, pre1, crit1 = _build(dev)                                # single process, whole batch
         loss1 = get_statistics(inputs, labels, model1, pre1, crit1, None, check="val", epoch=1)
