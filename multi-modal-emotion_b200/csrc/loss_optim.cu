@@ -134,21 +134,30 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (long long i = t; i < n4; i += stride) {
-        float4 pv = reinterpret_cast<float4*>(p)[i];
-        float4 mv = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
-        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    // Two float4 per array per thread and iteration, all eight loads issued before the first use; m, v and g are touched
+    // once per step (streaming loads / stores keep them from displacing the parameters and the bf16 mirror, which the next
+    // forward reads first, in L2).
+    auto ld = [](const float* q, long long i) { return __ldcs(reinterpret_cast<const float4*>(q) + i); };
+    auto update = [&](long long i, float4 pv, float4 mv, float4 vv, const float4 gv) {
         adam_one(pv.x, mv.x, vv.x, gv.x * gs, a);
         adam_one(pv.y, mv.y, vv.y, gv.y * gs, a);
         adam_one(pv.z, mv.z, vv.z, gv.z * gs, a);
         adam_one(pv.w, mv.w, vv.w, gv.w * gs, a);
         reinterpret_cast<float4*>(p)[i] = pv;
-        reinterpret_cast<float4*>(m)[i] = mv;
-        reinterpret_cast<float4*>(v)[i] = vv;
+        __stcs(reinterpret_cast<float4*>(m) + i, mv);
+        __stcs(reinterpret_cast<float4*>(v) + i, vv);
         if (p_bf16) reinterpret_cast<uint2*>(p_bf16)[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
-        if (a.zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.zero_grad) __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+    };
+    long long i = t;
+    for (; i + stride < n4; i += 2 * stride) {
+        const long long j = i + stride;
+        const float4 p0 = reinterpret_cast<float4*>(p)[i], p1 = reinterpret_cast<float4*>(p)[j];
+        const float4 m0 = ld(m, i), m1 = ld(m, j), v0 = ld(v, i), v1 = ld(v, j), g0 = ld(g, i), g1 = ld(g, j);
+        update(i, p0, m0, v0, g0);
+        update(j, p1, m1, v1, g1);
     }
+    if (i < n4) update(i, reinterpret_cast<float4*>(p)[i], ld(m, i), ld(v, i), ld(g, i));
     for (long long i = (n4 << 2) + t; i < n; i += stride) {
         float pv = p[i], mv = m[i], vv = v[i];
         adam_one(pv, mv, vv, g[i] * gs, a);
