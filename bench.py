@@ -540,7 +540,10 @@ def roofline_and_fusion(torch, L, syn, model, B, cfg, step_ms, peaks):
     peak = peaks["bf16_tflops"]
     traffic, traffic_of = None, None
     try:   # DRAM bytes per launch of the heaviest signature, from the committed `ncu --set full` capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_ncu_traffic.json")) as f:
+        tpath = os.path.join(ROOT, "profiles", "r2_gemm_ncu_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r1_gemm_ncu_traffic.json")
+        with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_of = tj["traffic_bytes"], {k: tj[k] for k in ("signature", "algorithmic_bytes", "source")}
     except Exception:  # noqa: BLE001
