@@ -51,9 +51,10 @@ def workload_name(cfg, B, variant):
     from multi_modal_emotion_b200 import synthetic as syn
 
     c = syn.CONFIGS[cfg]
-    return ("TAV MELD %d-class train step (PreFormer+TAVForMAE fwd, weighted CE, bwd, clip+AdamW), batch %d/GPU, "
+    shape = {"C1": "MELD", "C2": "MELD", "C3": "IEMOCAP-shape (15 s audio)", "C4": "MUStARD++-shape"}.get(cfg, cfg)
+    return ("TAV %s %d-class train step (PreFormer+TAVForMAE fwd, weighted CE, bwd, clip+AdamW), batch %d/GPU, "
             "T=%d, wav=%d samples, 16x3x224x224 video, fused S=%d, encoders=%s (random init)" % (
-                c["C"], B, c["T"], c["L"], syn.fused_len(cfg), variant))
+                shape, c["C"], B, c["T"], c["L"], syn.fused_len(cfg), variant))
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
